@@ -1,0 +1,241 @@
+// coalesce.cu — COO coalesce for sm_100a.
+//
+// Replaces torch_sparse.coalesce -> SparseStorage.__init__ (sort) + SparseStorage.coalesce()
+// (torch_sparse/coalesce.py:5-25, torch_sparse/storage.py:149-162, 436-466; value reduction =
+// torch_scatter.segment_csr, call site storage.py:451).
+//
+// The reference issues ~12-15 ATen kernels, 3-4 host syncs and builds the linearised key twice.
+// Here:  phase 1  key = row*N+col (+ "already sorted?" flag) -> [stable CUB radix sort over only
+//                 the significant key bits, 32-bit payload] -> head flags -> DeviceSelect gives the
+//                 run starts and E' on the device (copied to pinned host memory);
+//        phase 2  one kernel emits row'/col' from the run heads and reduces the values of each run
+//                 in sorted (== input, the sort is stable) order.
+// A stable sort makes the float 'add' order canonical (input order); the reference's order over
+// duplicates is unspecified (non-stable Tensor.sort, torch_sparse/utils.py:19-20).
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace tsb {
+
+__global__ void coalesce_keys_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
+                                     int64_t E, int64_t N, uint64_t* __restrict__ keys,
+                                     uint32_t* __restrict__ perm, int* __restrict__ unsorted) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride) {
+    const uint64_t k = (uint64_t)(row[i] * N + col[i]);
+    keys[i] = k;
+    perm[i] = (uint32_t)i;
+    if (i > 0) {
+      const uint64_t kp = (uint64_t)(__ldg(row + i - 1) * N + __ldg(col + i - 1));
+      bad |= k < kp;
+    }
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(unsorted, 1);
+}
+
+__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t E, uint8_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride)
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+
+__global__ void copy_count_kernel(const int* __restrict__ n_sel, int64_t* __restrict__ out) { *out = (int64_t)*n_sel; }
+
+__global__ void widen_perm_kernel(const uint32_t* __restrict__ perm, int64_t E, int64_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride) out[i] = (int64_t)perm[i];
+}
+
+enum { C_SUM = TSB200_SUM, C_MEAN = TSB200_MEAN, C_MIN = TSB200_MIN, C_MAX = TSB200_MAX };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+coalesce_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+                     const uint32_t* __restrict__ starts, int64_t E, int64_t N, int64_t n_unique,
+                     const T* __restrict__ value_in, int64_t D, int reduce, int64_t* __restrict__ row_out,
+                     int64_t* __restrict__ col_out, T* __restrict__ value_out, int64_t* __restrict__ perm_out) {
+  using acc_t = typename Traits<T>::acc_t;
+  const int64_t total = n_unique * (value_in ? D : 1);
+  const int64_t Dd = value_in ? D : 1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t seg = t / Dd, d = t - seg * Dd;
+    const int64_t s = starts[seg];
+    const int64_t e = (seg + 1 < n_unique) ? (int64_t)starts[seg + 1] : E;
+    if (d == 0) {
+      const uint64_t k = keys[s];
+      const uint64_t r = k / (uint64_t)N;
+      if (row_out) row_out[seg] = (int64_t)r;
+      if (col_out) col_out[seg] = (int64_t)(k - r * (uint64_t)N);
+      if (perm_out) perm_out[seg] = (int64_t)perm[s];
+    }
+    if (value_in) {
+      acc_t a = Traits<T>::to_acc(value_in[(int64_t)perm[s] * D + d]);
+      for (int64_t j = s + 1; j < e; j++) {
+        const acc_t v = Traits<T>::to_acc(value_in[(int64_t)perm[j] * D + d]);
+        if (reduce == C_SUM || reduce == C_MEAN) a = a + v;
+        else if (reduce == C_MIN) a = v < a ? v : a;
+        else a = v > a ? v : a;
+      }
+      if (reduce == C_MEAN) a = a / (acc_t)(e - s);
+      value_out[seg * D + d] = Traits<T>::from_acc(a);
+    }
+  }
+}
+
+struct CoLayout {
+  size_t k0, k1, p0, p1, flags, starts, scalars, cub, total;
+  size_t cub_bytes;
+  // scalars: [0] int unsorted, [1] int n_selected, [2..3] int64 n_unique, [4] int keys_cur, [5] int perm_cur
+};
+static CoLayout co_layout(int64_t E) {
+  CoLayout L;
+  const size_t n = (size_t)(E > 0 ? E : 1);
+  size_t off = 0;
+  L.scalars = off; off += 256;
+  L.k0 = off; off += align_up(n * 8, 256);
+  L.k1 = off; off += align_up(n * 8, 256);
+  L.p0 = off; off += align_up(n * 4, 256);
+  L.p1 = off; off += align_up(n * 4, 256);
+  L.flags = off; off += align_up(n, 256);
+  L.starts = off; off += align_up(n * 4, 256);
+  size_t t1 = 0, t2 = 0;
+  cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
+  cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, dk, dv, (int)n, 0, 64, (cudaStream_t)0);
+  cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr,
+                             (uint32_t*)nullptr, (int*)nullptr, (int)n, (cudaStream_t)0);
+  L.cub_bytes = t1 > t2 ? t1 : t2;
+  L.cub = off; off += align_up(L.cub_bytes, 256);
+  L.total = off;
+  return L;
+}
+
+static inline int cgrid(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace tsb
+
+using namespace tsb;
+
+extern "C" size_t tsb200_coalesce_workspace_bytes(int64_t E, int64_t M, int64_t N) {
+  (void)M; (void)N;
+  if (E < 0) return 0;
+  return co_layout(E).total;
+}
+
+// NOTE: synchronises `stream` once internally (to skip the sort when the input is already
+// sorted, like the reference's `(idx[1:] < idx[:-1]).any()` check, storage.py:154).
+extern "C" int tsb200_coalesce_sort(const int64_t* row, const int64_t* col, int64_t E, int64_t M, int64_t N,
+                                    void* workspace, size_t workspace_bytes, int64_t* n_unique_host,
+                                    void* stream) {
+  if (E < 0 || M < 0 || N < 0) return TSB200_ERR_INVALID_ARG;
+  if (E >= ((int64_t)1 << 31)) return TSB200_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const CoLayout L = co_layout(E);
+  if (!workspace || workspace_bytes < L.total) return TSB200_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  int* sc = (int*)(ws + L.scalars);
+  int64_t* n_unique_dev = (int64_t*)(ws + L.scalars + 8);
+  TSB_CUDA_TRY(cudaMemsetAsync(sc, 0, 256, st));
+  if (E == 0) {
+    if (n_unique_host) *n_unique_host = 0;
+    return 0;
+  }
+  if (!row || !col) return TSB200_ERR_INVALID_ARG;
+  uint64_t* k0 = (uint64_t*)(ws + L.k0); uint64_t* k1 = (uint64_t*)(ws + L.k1);
+  uint32_t* p0 = (uint32_t*)(ws + L.p0); uint32_t* p1 = (uint32_t*)(ws + L.p1);
+  coalesce_keys_kernel<<<cgrid(E), 256, 0, st>>>(row, col, E, N, k0, p0, sc);
+  TSB_LAUNCH_CHECK();
+  int unsorted = 0;
+  TSB_CUDA_TRY(cudaMemcpyAsync(&unsorted, sc, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TSB_CUDA_TRY(cudaStreamSynchronize(st));
+  int cur = 0;
+  if (unsorted) {
+    // significant bits of the largest possible key M*N-1
+    int bits = 1;
+    const unsigned __int128 maxkey = (unsigned __int128)(M > 0 ? M : 1) * (unsigned __int128)(N > 0 ? N : 1);
+    while (bits < 64 && ((unsigned __int128)1 << bits) < maxkey) bits++;
+    cub::DoubleBuffer<uint64_t> dk(k0, k1);
+    cub::DoubleBuffer<uint32_t> dv(p0, p1);
+    size_t tb = L.cub_bytes;
+    TSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, dk, dv, (int)E, 0, bits, st));
+    cur = (dk.Current() == k1) ? 1 : 0;
+    // CUB keeps keys and values in the same selector
+  }
+  int h[2] = {cur, cur};
+  TSB_CUDA_TRY(cudaMemcpyAsync(sc + 4, h, sizeof(h), cudaMemcpyHostToDevice, st));
+  const uint64_t* keys = cur ? k1 : k0;
+  uint8_t* flags = (uint8_t*)(ws + L.flags);
+  head_flags_kernel<<<cgrid(E), 256, 0, st>>>(keys, E, flags);
+  TSB_LAUNCH_CHECK();
+  size_t tb = L.cub_bytes;
+  TSB_CUDA_TRY(cub::DeviceSelect::Flagged(ws + L.cub, tb, cub::CountingInputIterator<uint32_t>(0), flags,
+                                          (uint32_t*)(ws + L.starts), sc + 1, (int)E, st));
+  copy_count_kernel<<<1, 1, 0, st>>>(sc + 1, n_unique_dev);
+  TSB_LAUNCH_CHECK();
+  if (n_unique_host)
+    TSB_CUDA_TRY(cudaMemcpyAsync(n_unique_host, n_unique_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" int tsb200_coalesce_emit(int64_t E, int64_t N, int64_t n_unique, const void* value_in, int64_t D,
+                                    int dtype, int reduce, int64_t* row_out, int64_t* col_out, void* value_out,
+                                    int64_t* perm_out, const void* workspace, void* stream) {
+  if (E < 0 || N < 0 || n_unique < 0 || n_unique > E) return TSB200_ERR_INVALID_ARG;
+  if (n_unique == 0) return 0;
+  if (!workspace) return TSB200_ERR_WORKSPACE;
+  if (value_in && (!value_out || D < 0)) return TSB200_ERR_INVALID_ARG;
+  if (value_in && (reduce < TSB200_SUM || reduce > TSB200_MAX)) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const CoLayout L = co_layout(E);
+  const char* ws = (const char*)workspace;
+  // which half of the double buffers holds the sorted data: recorded by phase 1 on the device;
+  // phase 1 already synchronised once and the caller synchronised to read E', so a tiny D2H here
+  // is a read of settled data.
+  int h[2] = {0, 0};
+  TSB_CUDA_TRY(cudaMemcpyAsync(h, ws + L.scalars + 16, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TSB_CUDA_TRY(cudaStreamSynchronize(st));
+  const uint64_t* keys = (const uint64_t*)(ws + (h[0] ? L.k1 : L.k0));
+  const uint32_t* perm = (const uint32_t*)(ws + (h[1] ? L.p1 : L.p0));
+  const uint32_t* starts = (const uint32_t*)(ws + L.starts);
+  if (value_in && D == 0) value_in = nullptr;
+  const int64_t total = n_unique * (value_in ? D : 1);
+  if (!value_in) {
+    coalesce_emit_kernel<float><<<cgrid(total), 256, 0, st>>>(keys, perm, starts, E, N, n_unique, nullptr, 1, reduce,
+                                                             row_out, col_out, nullptr, perm_out);
+    TSB_LAUNCH_CHECK();
+    return 0;
+  }
+  return dispatch_dtype(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    coalesce_emit_kernel<T><<<cgrid(total), 256, 0, st>>>(keys, perm, starts, E, N, n_unique, (const T*)value_in, D,
+                                                         reduce, row_out, col_out, (T*)value_out, perm_out);
+    TSB_LAUNCH_CHECK();
+    return 0;
+  });
+}
+
+extern "C" int tsb200_coalesce_perm(int64_t E, int64_t* perm_out, const void* workspace, void* stream) {
+  if (E < 0) return TSB200_ERR_INVALID_ARG;
+  if (E == 0) return 0;
+  if (!workspace) return TSB200_ERR_WORKSPACE;
+  if (!perm_out) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const CoLayout L = co_layout(E);
+  const char* ws = (const char*)workspace;
+  int h[2] = {0, 0};
+  TSB_CUDA_TRY(cudaMemcpyAsync(h, ws + L.scalars + 16, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TSB_CUDA_TRY(cudaStreamSynchronize(st));
+  const uint32_t* perm = (const uint32_t*)(ws + (h[1] ? L.p1 : L.p0));
+  widen_perm_kernel<<<cgrid(E), 256, 0, st>>>(perm, E, perm_out);
+  TSB_LAUNCH_CHECK();
+  return 0;
+}

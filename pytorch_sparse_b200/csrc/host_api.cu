@@ -1,0 +1,132 @@
+// host_api.cu — library-level entry points of libtsb200: version / error text / device check and
+// the HOST-buffer SpMM call (the end-to-end path a reference-side binding takes when it holds CPU
+// tensors, cf. spmm_cpu(rowptr, col, value, mat, reduce), csrc/cpu/spmm_cpu.cpp:8-11).
+//
+// tsb200_spmm_fw_host pipelines PCIe against the kernel: `mat` goes up first, then the CSR arrays
+// in row chunks; each chunk's SpMM starts as soon as its indices have landed and its output rows
+// are copied back on a second stream while later chunks are still uploading (PCIe is full duplex).
+#include <mutex>
+
+#include "common.cuh"
+
+namespace tsb {
+
+struct HostCtx {
+  std::mutex mu;
+  int device = -1;
+  char* buf = nullptr;
+  size_t cap = 0;
+  cudaStream_t s_up = nullptr, s_down = nullptr;
+  static constexpr int kMaxChunks = 16;
+  cudaEvent_t ev_chunk[kMaxChunks] = {};
+  bool init = false;
+};
+static HostCtx g_host;
+
+}  // namespace tsb
+
+using namespace tsb;
+
+extern "C" int tsb200_version(void) { return TSB200_VERSION; }
+
+extern "C" const char* tsb200_strerror(int code) {
+  switch (code) {
+    case 0: return "success";
+    case TSB200_ERR_INVALID_ARG: return "tsb200: invalid argument";
+    case TSB200_ERR_UNSUPPORTED: return "tsb200: unsupported dtype/reduce/extent combination";
+    case TSB200_ERR_WORKSPACE: return "tsb200: workspace missing or too small";
+    case TSB200_ERR_NO_DEVICE: return "tsb200: no sm_100 CUDA device";
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "tsb200: unknown error";
+}
+
+extern "C" int tsb200_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return TSB200_ERR_NO_DEVICE;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+    return TSB200_ERR_NO_DEVICE;
+  return major == 10 ? 0 : TSB200_ERR_NO_DEVICE;
+}
+
+extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* col_host, const void* value_host,
+                                   const void* mat_host, void* out_host, int64_t* arg_out_host, int64_t B,
+                                   int64_t M, int64_t N, int64_t K, int64_t E, int dtype, int reduce) {
+  if (B < 0 || M < 0 || N < 0 || K < 0 || E < 0) return TSB200_ERR_INVALID_ARG;
+  const size_t es = dtype_size(dtype);
+  if (!es) return TSB200_ERR_INVALID_ARG;
+  if (reduce < TSB200_SUM || reduce > TSB200_MAX) return TSB200_ERR_INVALID_ARG;
+  const bool arg = reduce == TSB200_MIN || reduce == TSB200_MAX;
+  if (B * M * K == 0) return 0;
+  if (!rowptr_host || !out_host || (arg && !arg_out_host)) return TSB200_ERR_INVALID_ARG;
+  if (E > 0 && (!col_host || !mat_host)) return TSB200_ERR_INVALID_ARG;
+  if (int rc = tsb200_device_ok()) return rc;
+
+  HostCtx& c = g_host;
+  std::lock_guard<std::mutex> lock(c.mu);
+  int dev = 0;
+  TSB_CUDA_TRY(cudaGetDevice(&dev));
+  if (!c.init || c.device != dev) {
+    TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_up, cudaStreamNonBlocking));
+    TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_down, cudaStreamNonBlocking));
+    for (int i = 0; i < HostCtx::kMaxChunks; i++)
+      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_chunk[i], cudaEventDisableTiming));
+    c.buf = nullptr; c.cap = 0; c.device = dev; c.init = true;
+  }
+  // device layout
+  const size_t ws_bytes = tsb200_spmm_fw_workspace_bytes(B, M, K, E, dtype, reduce);
+  size_t off = 0;
+  const size_t o_rowptr = off; off += align_up((size_t)(M + 1) * 8, 256);
+  const size_t o_col = off; off += align_up((size_t)(E > 0 ? E : 1) * 8 + 1024, 256);
+  const size_t o_val = off; off += align_up((size_t)(E > 0 ? E : 1) * es + 1024, 256);
+  const size_t o_mat = off; off += align_up((size_t)B * N * K * es, 256);
+  const size_t o_out = off; off += align_up((size_t)B * M * K * es, 256);
+  const size_t o_arg = off; off += arg ? align_up((size_t)B * M * K * 8, 256) : 0;
+  const size_t o_ws = off; off += align_up(ws_bytes, 256);
+  if (off > c.cap) {
+    if (c.buf) TSB_CUDA_TRY(cudaFree(c.buf));
+    c.buf = nullptr; c.cap = 0;
+    TSB_CUDA_TRY(cudaMalloc(&c.buf, off));
+    c.cap = off;
+  }
+  char* d = c.buf;
+  int64_t* d_rowptr = (int64_t*)(d + o_rowptr);
+  int64_t* d_col = (int64_t*)(d + o_col);
+  void* d_val = value_host ? (void*)(d + o_val) : nullptr;
+
+  TSB_CUDA_TRY(cudaMemcpyAsync(d + o_mat, mat_host, (size_t)B * N * K * es, cudaMemcpyHostToDevice, c.s_up));
+  TSB_CUDA_TRY(cudaMemcpyAsync(d_rowptr, rowptr_host, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, c.s_up));
+
+  // chunking only pays (and only keeps out/arg_out contiguous per copy) for a single batch
+  int nchunk = (B == 1 && M >= 4096 && E >= (1 << 20)) ? 8 : 1;
+  for (int ch = 0; ch < nchunk; ch++) {
+    const int64_t r0 = M * ch / nchunk, r1 = M * (ch + 1) / nchunk;
+    const int64_t e0 = rowptr_host[r0], e1 = rowptr_host[r1];
+    if (e1 > e0) {
+      TSB_CUDA_TRY(cudaMemcpyAsync(d_col + e0, col_host + e0, (size_t)(e1 - e0) * 8, cudaMemcpyHostToDevice, c.s_up));
+      if (value_host)
+        TSB_CUDA_TRY(cudaMemcpyAsync((char*)d_val + e0 * es, (const char*)value_host + e0 * es,
+                                     (size_t)(e1 - e0) * es, cudaMemcpyHostToDevice, c.s_up));
+    }
+    if (r1 > r0) {
+      int rc = tsb200_spmm_fw(d_rowptr + r0, d_col, d_val, d + o_mat, d + o_out + (size_t)r0 * K * es,
+                              arg ? (int64_t*)(d + o_arg) + r0 * K : nullptr, B, r1 - r0, N, K, E, dtype, reduce,
+                              ws_bytes ? d + o_ws : nullptr, ws_bytes, c.s_up);
+      if (rc) return rc;
+    }
+    TSB_CUDA_TRY(cudaEventRecord(c.ev_chunk[ch], c.s_up));
+    TSB_CUDA_TRY(cudaStreamWaitEvent(c.s_down, c.ev_chunk[ch], 0));
+    if (r1 > r0) {
+      const size_t rows = (size_t)(nchunk == 1 ? B * M : (r1 - r0));
+      TSB_CUDA_TRY(cudaMemcpyAsync((char*)out_host + (size_t)r0 * K * es, d + o_out + (size_t)r0 * K * es,
+                                   rows * K * es, cudaMemcpyDeviceToHost, c.s_down));
+      if (arg)
+        TSB_CUDA_TRY(cudaMemcpyAsync(arg_out_host + r0 * K, (int64_t*)(d + o_arg) + r0 * K, rows * K * 8,
+                                     cudaMemcpyDeviceToHost, c.s_down));
+    }
+  }
+  TSB_CUDA_TRY(cudaStreamSynchronize(c.s_up));
+  TSB_CUDA_TRY(cudaStreamSynchronize(c.s_down));
+  return 0;
+}

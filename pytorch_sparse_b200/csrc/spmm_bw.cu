@@ -1,0 +1,259 @@
+// spmm_bw.cu — SpMM backward kernels for sm_100a.
+//
+//  * tsb200_spmm_value_bw: SDDMM  out[e] = sum_b <mat[b,col[e],:], grad[b,row[e],:]>
+//    replaces spmm_value_bw_cpu / spmm_value_bw_kernel
+//    (csrc/cpu/spmm_cpu.cpp:103-152, csrc/cuda/spmm_cuda.cu:157-237).
+//    nnz-parallel (perfect balance on power-law rows): a warp takes 32 consecutive nnz, reads
+//    row/col coalesced, LPR lanes x 16 B cover one dense row, the 32/LPR lane groups work on
+//    different nnz, results are gathered back to one lane per nnz for a coalesced store.
+//    grad[row[e]] is re-read per nnz but consecutive nnz share the row => L1/L2 hits.
+//  * tsb200_spmm_minmax_bw: fused replacement of the 8-op ATen chain of SPMMMin/SPMMMax::backward
+//    (csrc/spmm.cpp:204-242, 264-302): one pass over arg_out, atomics into zero-filled fp32/fp64
+//    accumulators.
+#include "common.cuh"
+
+namespace tsb {
+
+template <typename T, int VEC> struct Vec16;
+template <> struct Vec16<float, 4> {
+  static __device__ __forceinline__ float dot(const uint4& a, const uint4& b) {
+    return __uint_as_float(a.x) * __uint_as_float(b.x) + __uint_as_float(a.y) * __uint_as_float(b.y) +
+           __uint_as_float(a.z) * __uint_as_float(b.z) + __uint_as_float(a.w) * __uint_as_float(b.w);
+  }
+};
+template <> struct Vec16<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ float dot(const uint4& a, const uint4& b) {
+    const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      s = fmaf(__uint_as_float(x[i] << 16), __uint_as_float(y[i] << 16), s);
+      s = fmaf(__uint_as_float(x[i] & 0xffff0000u), __uint_as_float(y[i] & 0xffff0000u), s);
+    }
+    return s;
+  }
+};
+template <> struct Vec16<__half, 8> {
+  static __device__ __forceinline__ float dot(const uint4& a, const uint4& b) {
+    const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&x[i]));
+      const float2 q = __half22float2(*reinterpret_cast<const __half2*>(&y[i]));
+      s = fmaf(p.x, q.x, s);
+      s = fmaf(p.y, q.y, s);
+    }
+    return s;
+  }
+};
+
+// vector path: K*sizeof(T) % 16 == 0, 16 B aligned mat/grad.
+template <typename T, int LPR, int U>
+__global__ void __launch_bounds__(256)
+value_bw_vec_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ rowptr,
+                    const int64_t* __restrict__ col, const T* __restrict__ mat,
+                    const T* __restrict__ grad, T* __restrict__ out, int64_t B, int64_t M, int64_t N,
+                    int64_t K, int64_t E, bool mean) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, li = lane % LPR;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nvec = K / VEC;  // 16-byte vectors per dense row
+  const int64_t row_bytes = K * (int64_t)sizeof(T);
+  const uint64_t pol = make_policy_evict_last();
+
+  for (int64_t e0 = wid * 32; e0 < E; e0 += nw * 32) {
+    const int64_t e = e0 + lane;
+    const bool valid = e < E;
+    const int64_t r = valid ? __ldg(row + e) : 0;
+    const int64_t c = valid ? __ldg(col + e) : 0;
+    float res = 0.f;  // lane `j` ends up with the result of nnz e0 + j
+    for (int64_t b = 0; b < B; b++) {
+      const char* matb = (const char*)mat + b * N * row_bytes;
+      const char* gradb = (const char*)grad + b * M * row_bytes;
+#pragma unroll 1
+      for (int s0 = 0; s0 < 32; s0 += U * G) {
+        float part[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int j = s0 + u * G + g;  // nnz handled by this group in this step
+          const int64_t rj = __shfl_sync(0xffffffffu, r, j);
+          const int64_t cj = __shfl_sync(0xffffffffu, c, j);
+          const bool act = (e0 + j) < E;
+          float s = 0.f;
+          if (act) {
+            for (int64_t v = li; v < nvec; v += LPR) {
+              const uint4 a = ldg128_hint(matb + cj * row_bytes + v * 16, pol);
+              const uint4 q = ldg128(gradb + rj * row_bytes + v * 16);
+              s += Vec16<T, VEC>::dot(a, q);
+            }
+          }
+          part[u] = s;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          float s = part[u];
+#pragma unroll
+          for (int off = LPR >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+          // group g's lanes now all hold the dot of nnz j = s0 + u*G + g; hand it to lane j
+          const int j_of_lane = lane;  // lane j wants group (j - s0 - u*G) if in range
+          const int gg = j_of_lane - s0 - u * G;
+          const float got = __shfl_sync(0xffffffffu, s, (gg >= 0 && gg < G) ? gg * LPR : 0);
+          if (gg >= 0 && gg < G) res += got;
+        }
+      }
+    }
+    if (valid) {
+      if (mean) {
+        const int64_t cnt = __ldg(rowptr + r + 1) - __ldg(rowptr + r);
+        res = res / (float)(cnt > 0 ? cnt : 1);
+      }
+      out[e] = Traits<T>::from_acc(res);
+    }
+  }
+}
+
+// generic: warp per nnz, lanes stride over k (any dtype / alignment).
+template <typename T>
+__global__ void __launch_bounds__(256)
+value_bw_generic_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ rowptr,
+                        const int64_t* __restrict__ col, const T* __restrict__ mat,
+                        const T* __restrict__ grad, T* __restrict__ out, int64_t B, int64_t M,
+                        int64_t N, int64_t K, int64_t E, bool mean) {
+  using acc_t = typename Traits<T>::acc_t;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t e = wid; e < E; e += nw) {
+    const int64_t r = row[e], c = col[e];
+    acc_t s = (acc_t)0;
+    for (int64_t b = 0; b < B; b++) {
+      const T* mp = mat + (b * N + c) * K;
+      const T* gp = grad + (b * M + r) * K;
+      for (int64_t k = lane; k < K; k += 32) s += Traits<T>::to_acc(mp[k]) * Traits<T>::to_acc(gp[k]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+      if (mean) {
+        const int64_t cnt = rowptr[r + 1] - rowptr[r];
+        s = s / (acc_t)(cnt > 0 ? cnt : 1);
+      }
+      out[e] = Traits<T>::from_acc(s);
+    }
+  }
+}
+
+template <typename T, typename A>
+__global__ void __launch_bounds__(256)
+minmax_bw_kernel(const int64_t* __restrict__ col, const T* __restrict__ value, const T* __restrict__ mat,
+                 const T* __restrict__ grad_out, const int64_t* __restrict__ arg_out,
+                 A* __restrict__ grad_value, A* __restrict__ grad_mat, int64_t B, int64_t M, int64_t N,
+                 int64_t K, int64_t E) {
+  const int64_t total = B * M * K;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t a = arg_out[i];
+    if (a < 0 || a >= E) continue;  // sentinel E: empty row (csrc/spmm.cpp:270-271)
+    const int64_t k = i % K;
+    const int64_t b = i / (M * K);
+    const A g = (A)Traits<T>::to_acc(grad_out[i]);
+    const int64_t c = col[a];
+    const int64_t mi = (b * N + c) * K + k;
+    if (grad_value) atomicAdd(grad_value + a, (A)Traits<T>::to_acc(mat[mi]) * g);
+    if (grad_mat) atomicAdd(grad_mat + mi, value ? (A)Traits<T>::to_acc(value[a]) * g : g);
+  }
+}
+
+template <typename T, int LPR, int U>
+static int launch_value_vec(const int64_t* row, const int64_t* rowptr, const int64_t* col, const void* mat,
+                            const void* grad, void* out, int64_t B, int64_t M, int64_t N, int64_t K,
+                            int64_t E, bool mean, cudaStream_t st) {
+  int64_t blocks = (E + 255) / 256;  // 8 warps x 32 nnz per CTA pass
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  value_bw_vec_kernel<T, LPR, U><<<(int)blocks, 256, 0, st>>>(row, rowptr, col, (const T*)mat, (const T*)grad,
+                                                             (T*)out, B, M, N, K, E, mean);
+  TSB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int dispatch_value_vec(const int64_t* row, const int64_t* rowptr, const int64_t* col, const void* mat,
+                              const void* grad, void* out, int64_t B, int64_t M, int64_t N, int64_t K,
+                              int64_t E, bool mean, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t vecs = K / VEC;
+#define TSB_ARGS row, rowptr, col, mat, grad, out, B, M, N, K, E, mean, st
+  if (vecs <= 1) return launch_value_vec<T, 1, 1>(TSB_ARGS);
+  if (vecs <= 4) return launch_value_vec<T, 4, 2>(TSB_ARGS);
+  if (vecs <= 8) return launch_value_vec<T, 8, 2>(TSB_ARGS);
+  if (vecs <= 16) return launch_value_vec<T, 16, 4>(TSB_ARGS);
+  return launch_value_vec<T, 32, 4>(TSB_ARGS);
+#undef TSB_ARGS
+}
+
+}  // namespace tsb
+
+using namespace tsb;
+
+extern "C" int tsb200_spmm_value_bw(const int64_t* row, const int64_t* rowptr, const int64_t* col,
+                                    const void* mat, const void* grad, void* out, int64_t B, int64_t M,
+                                    int64_t N, int64_t K, int64_t E, int dtype, int reduce, void* stream) {
+  if (B < 0 || M < 0 || N < 0 || K < 0 || E < 0) return TSB200_ERR_INVALID_ARG;
+  if (reduce != TSB200_SUM && reduce != TSB200_MEAN) return TSB200_ERR_INVALID_ARG;
+  if (dtype_size(dtype) == 0) return TSB200_ERR_INVALID_ARG;
+  if (E == 0) return 0;
+  if (!row || !rowptr || !col || !out) return TSB200_ERR_INVALID_ARG;
+  if (B * K > 0 && (!mat || !grad)) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool mean = reduce == TSB200_MEAN;
+  const size_t es = dtype_size(dtype);
+  const bool vec = (dtype == TSB200_F32 || dtype == TSB200_F16 || dtype == TSB200_BF16) && K > 0 &&
+                   (K * es) % 16 == 0 && !((uintptr_t)mat & 15) && !((uintptr_t)grad & 15);
+  if (vec) {
+    switch (dtype) {
+      case TSB200_F32: return dispatch_value_vec<float>(row, rowptr, col, mat, grad, out, B, M, N, K, E, mean, st);
+      case TSB200_F16: return dispatch_value_vec<__half>(row, rowptr, col, mat, grad, out, B, M, N, K, E, mean, st);
+      case TSB200_BF16:
+        return dispatch_value_vec<__nv_bfloat16>(row, rowptr, col, mat, grad, out, B, M, N, K, E, mean, st);
+    }
+  }
+  return dispatch_dtype(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    int64_t blocks = (E + 7) / 8;
+    const int64_t cap = (int64_t)kNumSMs * 32;
+    if (blocks > cap) blocks = cap;
+    value_bw_generic_kernel<T><<<(int)blocks, 256, 0, st>>>(row, rowptr, col, (const T*)mat, (const T*)grad,
+                                                           (T*)out, B, M, N, K, E, mean);
+    TSB_LAUNCH_CHECK();
+    return 0;
+  });
+}
+
+extern "C" int tsb200_spmm_minmax_bw(const int64_t* col, const void* value, const void* mat,
+                                     const void* grad_out, const int64_t* arg_out, void* grad_value,
+                                     void* grad_mat, int64_t B, int64_t M, int64_t N, int64_t K, int64_t E,
+                                     int dtype, void* stream) {
+  if (B < 0 || M < 0 || N < 0 || K < 0 || E < 0) return TSB200_ERR_INVALID_ARG;
+  if (B * M * K == 0 || E == 0) return 0;
+  if (!col || !grad_out || !arg_out) return TSB200_ERR_INVALID_ARG;
+  if (grad_value && !mat) return TSB200_ERR_INVALID_ARG;
+  if (!grad_value && !grad_mat) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = B * M * K;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  return dispatch_float_dtype(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    using A = typename std::conditional<std::is_same<T, double>::value, double, float>::type;
+    minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
+                                                       arg_out, (A*)grad_value, (A*)grad_mat, B, M, N, K, E);
+    TSB_LAUNCH_CHECK();
+    return 0;
+  });
+}

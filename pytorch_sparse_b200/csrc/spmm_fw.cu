@@ -1,0 +1,727 @@
+// spmm_fw.cu — CSR SpMM forward for sm_100a.
+//
+// Replaces spmm_fw -> spmm_cpu / spmm_cuda of the reference
+// (csrc/spmm.cpp:22-35, csrc/cpu/spmm_cpu.cpp:8-101, csrc/cuda/spmm_cuda.cu:13-155).
+//
+// Design (row-split CSR, HBM/L2-gather bound):
+//   * work item = 32 consecutive rows, pulled by a WARP from a global atomic counter
+//     (persistent grid: 148 SMs x resident CTAs);
+//   * the item's rowptr slice lives in lane registers (one coalesced 264 B read);
+//   * col/value of the item's contiguous nnz range stream through a per-warp shared-memory
+//     ring filled by cp.async (LDGSTS) 32-entry windows, issued 2 windows ahead of use, so the
+//     index stream is read exactly once, fully coalesced, and never stalls the gathers;
+//   * the dense operand is gathered with 128-bit loads: LPR lanes x 16 B cover one row of
+//     `mat` (CH chunks if a row is wider than 512 B); the 32/LPR lane groups of a warp work on
+//     different nnz of the same row, U gathers in flight per lane; fp32 accumulation;
+//   * groups are combined with __shfl_xor, consecutive lanes own consecutive 16 B column
+//     vectors => fully coalesced 128-bit streaming stores;
+//   * load balance for power-law rows: rows longer than LONG_T nnz and rows beyond an
+//     item's nnz budget are deferred into a device-side segment queue (<= SEG nnz each); a
+//     second kernel runs one warp per segment, a third combines multi-segment rows in
+//     segment order (deterministic; min/max keep the smallest-e tie-break).
+//   * anything the vector path cannot take (K*sizeof(T) % 16 != 0, integer / fp64 types,
+//     unaligned pointers, E >= 2^31) goes to a generic lane-per-column kernel that walks the
+//     nnz sequentially exactly like csrc/cpu/spmm_cpu.cpp:75-88 (bit-identical for fp32/fp64).
+#include "common.cuh"
+
+namespace tsb {
+
+enum : int { R_SUM = TSB200_SUM, R_MEAN = TSB200_MEAN, R_MIN = TSB200_MIN, R_MAX = TSB200_MAX };
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kRing = 128;      // entries per warp ring (4 windows of 32)
+constexpr int kPrefetch = 2;    // windows issued ahead of the one being consumed
+constexpr int kLongT = 256;     // rows longer than this are split into segments
+constexpr int kSeg = 256;       // nnz per segment
+constexpr int kItemCap = 1024;  // nnz budget of one 32-row work item before rows are deferred
+
+struct Segment {      // 32 B
+  int64_t row_b;      // b * M + row
+  int64_t start, end; // absolute nnz range
+  int64_t slot;       // partial slot, or -1: single-segment row, finalise directly
+};
+struct LongRow {      // 24 B
+  int64_t row_b;
+  int64_t first_slot;
+  int64_t nseg_count;  // (nseg << 40) | count   (count = row degree < 2^40)
+};
+
+struct SpmmParams {
+  const int64_t* rowptr;
+  const int64_t* col;
+  const void* value;
+  const void* mat;
+  void* out;
+  int64_t* arg_out;
+  int64_t B, M, N, K, E;
+  int mean;  // SUM kernels: divide by max(count,1) at the end
+  int k0;  // first column handled by this launch (column tiling for very wide K)
+  // workspace
+  unsigned int* counters;  // [0] item counter, [1] #segments, [2] #long rows, [3] #partial slots
+  Segment* segs;
+  LongRow* longs;
+  void* part_val;      // acc_t [slots, K]
+  int64_t* part_arg;   // int64 [slots, K] (min/max)
+  int64_t seg_cap, long_cap, slot_cap;
+};
+
+// ---- per-warp streaming index ring ------------------------------------------------------------
+template <typename T> struct IndexRing {
+  bool has_val;
+  int64_t* s_col;
+  T* s_val;
+  const int64_t* col;
+  const T* val;
+  int64_t base;   // absolute nnz index of ring-relative 0 (multiple of 32)
+  int64_t limit;  // absolute end of valid data (E)
+  int issued_w;   // last window issued
+  int ready_w;    // windows <= ready_w are complete and visible to the whole warp
+
+  __device__ __forceinline__ void reset(int64_t base_) {
+    base = base_;
+    issued_w = -0x40000000;
+    ready_w = -0x40000000;
+  }
+  __device__ __forceinline__ void issue(int w, int lane) {
+    const int64_t abs0 = base + (int64_t)w * 32;
+    int64_t* dcol = s_col + ((w & 3) << 5);
+    {
+      const int64_t a = abs0 + lane;
+      const bool ok = a < limit;
+      cp_async_zfill<8>(dcol + lane, ok ? (const void*)(col + a) : (const void*)col, ok ? 8 : 0);
+    }
+    if (has_val) {
+      T* dval = s_val + ((w & 3) << 5);
+      if constexpr (sizeof(T) >= 4) {
+        const int64_t a = abs0 + lane;
+        const bool ok = a < limit;
+        cp_async_zfill<sizeof(T)>(dval + lane,
+                                                          ok ? (const void*)(val + a) : (const void*)val,
+                                                          ok ? (int)sizeof(T) : 0);
+      } else {
+        constexpr int EPL = 4 / sizeof(T);  // entries per lane copy
+        if (lane < 32 / EPL) {
+          const int64_t a = abs0 + (int64_t)lane * EPL;
+          int64_t rem = limit - a;
+          int nb = rem <= 0 ? 0 : (rem >= EPL ? 4 : (int)rem * (int)sizeof(T));
+          cp_async_zfill<4>(dval + lane * EPL, nb ? (const void*)(val + a) : (const void*)val, nb);
+        }
+      }
+    }
+    cp_async_commit();
+  }
+  // make ring-relative entries [lo_rel, hi_rel) readable (hi_rel - lo_rel <= 32)
+  __device__ __forceinline__ void ensure(int lo_rel, int hi_rel, int lane) {
+    const int need_w = (hi_rel - 1) >> 5;
+    if (need_w <= ready_w) return;
+    const int low_w = lo_rel >> 5;
+    if (issued_w < need_w + kPrefetch) {
+      __syncwarp();  // every lane is done reading the windows about to be overwritten
+      if (issued_w < low_w - 1) issued_w = low_w - 1;
+      while (issued_w < need_w + kPrefetch) issue(++issued_w, lane);
+    }
+    cp_async_wait<kPrefetch>();
+    __syncwarp();
+    ready_w = issued_w - kPrefetch;
+  }
+};
+
+// ---- accumulator helpers -----------------------------------------------------------------------
+template <typename T, int VEC> struct Unpack;
+template <> struct Unpack<float, 4> {
+  static __device__ __forceinline__ void run(const uint4& d, float* f) {
+    f[0] = __uint_as_float(d.x); f[1] = __uint_as_float(d.y);
+    f[2] = __uint_as_float(d.z); f[3] = __uint_as_float(d.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+  }
+};
+template <> struct Unpack<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void run(const uint4& d, float* f) {
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Unpack<__half, 8> {
+  static __device__ __forceinline__ void run(const uint4& d, float* f) {
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ uint4 pack(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// round an fp32 product to the storage type and back (min/max compare on the rounded product,
+// as the reference does: csrc/cpu/spmm_cpu.cpp:81-83 computes `val * mat` in scalar_t).
+template <typename T> __device__ __forceinline__ float round_to(float x) { return x; }
+template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+template <> __device__ __forceinline__ float round_to<__half>(float x) {
+  return __half2float(__float2half_rn(x));
+}
+
+template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
+  static constexpr int VEC = 16 / sizeof(T);
+  static constexpr int G = 32 / LPR;
+  static constexpr int NA = VEC * CH;
+  static constexpr bool ARG = (RED == R_MIN || RED == R_MAX);
+
+  float acc[NA];
+  int arg[ARG ? NA : 1];
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+      if (RED == R_MIN) acc[i] = Traits<T>::to_acc(Traits<T>::highest());
+      else if (RED == R_MAX) acc[i] = Traits<T>::to_acc(Traits<T>::lowest());
+      else acc[i] = 0.f;
+    }
+    if (ARG) {
+#pragma unroll
+      for (int i = 0; i < NA; i++) arg[i] = 0x7fffffff;
+    }
+  }
+
+  // accumulate ring-relative nnz [s, e) of one row; `matb` already points at this lane's
+  // first column of batch b.
+  __device__ __forceinline__ void accumulate(IndexRing<T>& ring, int s, int e,
+                                             const char* __restrict__ matb, int64_t row_bytes,
+                                             bool col_ok[CH], int lane, int g, uint64_t pol) {
+    for (int j0 = s; j0 < e; j0 += U * G) {
+      const int jend = min(e, j0 + U * G);
+      ring.ensure(j0, jend, lane);
+      uint4 d[U][CH];
+      float v[U];
+      bool act[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int j = j0 + u * G + g;
+        act[u] = j < jend;
+        const int slot = j & (kRing - 1);
+        const int64_t c = ring.s_col[slot];
+        // inactive lanes must contribute exactly +0 (stale ring bytes may be NaN/Inf)
+        v[u] = act[u] ? (ring.has_val ? Traits<T>::to_acc(ring.s_val[slot]) : 1.f) : 0.f;
+        const char* src = matb + c * row_bytes;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+          if (act[u] && col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
+          else d[u][ch] = make_uint4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int jabs = (int)((ring.base + j0 + u * G + g));  // absolute nnz index (E < 2^31)
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+          float f[VEC];
+          Unpack<T, VEC>::run(d[u][ch], f);
+#pragma unroll
+          for (int i = 0; i < VEC; i++) {
+            if (RED == R_SUM) {
+              // inactive lanes carry d = 0 => contribute +0
+              acc[ch * VEC + i] = fmaf(v[u], f[i], acc[ch * VEC + i]);  // v == 1 when has_value=false
+            } else {
+              const float p = round_to<T>(v[u] * f[i]);  // v == 1 => p == f exactly
+              const bool better = (RED == R_MIN) ? (p < acc[ch * VEC + i]) : (p > acc[ch * VEC + i]);
+              if (act[u] && better) {
+                acc[ch * VEC + i] = p;
+                arg[ch * VEC + i] = jabs;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // combine the G lane groups; afterwards group 0 holds the row result.
+  __device__ __forceinline__ void reduce_groups() {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < NA; i++) {
+        const float ov = __shfl_xor_sync(0xffffffffu, acc[i], off);
+        if (RED == R_SUM) {
+          acc[i] += ov;
+        } else {
+          const int oa = __shfl_xor_sync(0xffffffffu, arg[i], off);
+          const bool better = (RED == R_MIN) ? (ov < acc[i]) : (ov > acc[i]);
+          if (better || (ov == acc[i] && oa < arg[i])) {
+            acc[i] = ov;
+            arg[i] = oa;
+          }
+        }
+      }
+    }
+  }
+
+  // final write of one row (group 0 lanes). count = row degree.
+  __device__ __forceinline__ void store_row(T* __restrict__ out_row, int64_t* __restrict__ arg_row,
+                                            int64_t count, int64_t E, bool col_ok[CH], int li,
+                                            bool mean) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ch++) {
+      if (!col_ok[ch]) continue;
+      float f[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; i++) {
+        float a = acc[ch * VEC + i];
+        if (RED == R_SUM && mean) a = a / (float)(count > 0 ? count : 1);
+        if (ARG && count == 0) a = 0.f;
+        f[i] = a;
+      }
+      const int koff = (ch * LPR + li) * VEC;
+      stg128_stream(out_row + koff, Unpack<T, VEC>::pack(f));
+      if (ARG) {
+#pragma unroll
+        for (int i = 0; i < VEC; i += 2) {
+          longlong2 a2;
+          a2.x = (count > 0 && arg[ch * VEC + i] != 0x7fffffff) ? (int64_t)arg[ch * VEC + i] : E;
+          a2.y = (count > 0 && arg[ch * VEC + i + 1] != 0x7fffffff) ? (int64_t)arg[ch * VEC + i + 1] : E;
+          stg128_stream(arg_row + koff + i, *reinterpret_cast<uint4*>(&a2));
+        }
+      }
+    }
+  }
+};
+
+template <typename T, int RED, int LPR, int CH, int U>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_vec_kernel(const SpmmParams p) {
+  using Eng = RowEngine<T, RED, LPR, CH, U>;
+  constexpr int VEC = Eng::VEC;
+  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRing];
+  __shared__ __align__(16) T s_val[kWarpsPerCta][kRing];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LPR, li = lane % LPR;
+
+  IndexRing<T> ring;
+  ring.s_col = s_col[warp];
+  ring.s_val = s_val[warp];
+  ring.has_val = p.value != nullptr;
+  ring.col = p.col;
+  ring.val = (const T*)p.value;
+  ring.limit = p.E;
+  const uint64_t pol = make_policy_evict_last();
+
+  bool col_ok[CH];
+#pragma unroll
+  for (int ch = 0; ch < CH; ch++) col_ok[ch] = p.k0 + (ch * LPR + li) * VEC < p.K;
+  const int64_t row_bytes = p.K * (int64_t)sizeof(T);
+  const int64_t lane_off = ((int64_t)p.k0 + (int64_t)li * VEC) * (int64_t)sizeof(T);
+
+  const int64_t nblk = (p.M + 31) >> 5;
+  const int64_t n_items = nblk * p.B;
+
+  unsigned int item = 0;
+  if (lane == 0) item = atomicAdd(&p.counters[0], 1u);
+  item = __shfl_sync(0xffffffffu, item, 0);
+
+  while ((int64_t)item < n_items) {
+    unsigned int next_item = 0;
+    if (lane == 0) next_item = atomicAdd(&p.counters[0], 1u);  // latency hidden behind this item
+
+    const int64_t b = item / nblk, blk = item - b * nblk;
+    const int64_t r0 = blk << 5;
+    const int nrows = (int)min((int64_t)32, p.M - r0);
+    const int64_t rp0 = __ldg(p.rowptr + r0 + min(lane, nrows));
+    const int64_t rp1 = __ldg(p.rowptr + r0 + min(lane + 1, nrows));
+    const int64_t a0 = __shfl_sync(0xffffffffu, rp0, 0);
+    const int64_t base = a0 & ~(int64_t)31;
+    const int s_rel = (int)(rp0 - base), e_rel = (int)(rp1 - base);
+    const int deg = e_rel - s_rel;
+
+    // nnz budget: prefix sum of the degrees of the non-long rows
+    const bool is_long = deg > kLongT;
+    int cum = is_long ? 0 : deg;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, cum, off);
+      if (lane >= off) cum += t;
+    }
+    const bool defer = (deg > 0) && (is_long || cum > kItemCap);
+    const unsigned defer_mask = __ballot_sync(0xffffffffu, defer);
+
+    if (defer) {  // rare: push this row's segments
+      const int nseg = (deg + kSeg - 1) / kSeg;
+      const unsigned seg0 = atomicAdd(&p.counters[1], (unsigned)nseg);
+      int64_t slot0 = -1;
+      if (nseg > 1) {
+        slot0 = atomicAdd(&p.counters[3], (unsigned)nseg);
+        const unsigned lr = atomicAdd(&p.counters[2], 1u);
+        if ((int64_t)lr < p.long_cap) {
+          LongRow L;
+          L.row_b = b * p.M + r0 + lane;
+          L.first_slot = slot0;
+          L.nseg_count = ((int64_t)nseg << 40) | (int64_t)deg;
+          p.longs[lr] = L;
+        }
+      }
+      for (int sgi = 0; sgi < nseg; sgi++) {
+        if ((int64_t)seg0 + sgi < p.seg_cap) {
+          Segment S;
+          S.row_b = b * p.M + r0 + lane;
+          S.start = rp0 + (int64_t)sgi * kSeg;
+          S.end = min(rp1, S.start + kSeg);
+          S.slot = slot0 < 0 ? -1 : slot0 + sgi;
+          p.segs[seg0 + sgi] = S;
+        }
+      }
+    }
+    __syncwarp();
+
+    ring.reset(base);
+    const char* matb = (const char*)p.mat + b * p.N * row_bytes + lane_off;
+    T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0;
+    int64_t* argb = p.arg_out ? p.arg_out + (b * p.M + r0) * p.K + p.k0 : nullptr;
+
+    for (int rl = 0; rl < nrows; rl++) {
+      if ((defer_mask >> rl) & 1u) continue;
+      const int s = __shfl_sync(0xffffffffu, s_rel, rl);
+      const int e = __shfl_sync(0xffffffffu, e_rel, rl);
+      Eng eng;
+      eng.init();
+      eng.accumulate(ring, s, e, matb, row_bytes, col_ok, lane, g, pol);
+      eng.reduce_groups();
+      if (g == 0) eng.store_row(outb + (int64_t)rl * p.K, argb ? argb + (int64_t)rl * p.K : nullptr, e - s, p.E, col_ok, li, p.mean != 0);
+    }
+    item = __shfl_sync(0xffffffffu, next_item, 0);
+  }
+}
+
+// one warp per queued segment
+template <typename T, int RED, int LPR, int CH, int U>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+spmm_seg_kernel(const SpmmParams p) {
+  using Eng = RowEngine<T, RED, LPR, CH, U>;
+  constexpr int VEC = Eng::VEC;
+  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRing];
+  __shared__ __align__(16) T s_val[kWarpsPerCta][kRing];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LPR, li = lane % LPR;
+
+  IndexRing<T> ring;
+  ring.s_col = s_col[warp];
+  ring.s_val = s_val[warp];
+  ring.has_val = p.value != nullptr;
+  ring.col = p.col;
+  ring.val = (const T*)p.value;
+  ring.limit = p.E;
+  const uint64_t pol = make_policy_evict_last();
+
+  bool col_ok[CH];
+#pragma unroll
+  for (int ch = 0; ch < CH; ch++) col_ok[ch] = p.k0 + (ch * LPR + li) * VEC < p.K;
+  const int64_t row_bytes = p.K * (int64_t)sizeof(T);
+  const int64_t lane_off = ((int64_t)p.k0 + (int64_t)li * VEC) * (int64_t)sizeof(T);
+
+  const int64_t nseg = min((int64_t)p.counters[1], p.seg_cap);
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t sidx = (int64_t)blockIdx.x * kWarpsPerCta + warp; sidx < nseg; sidx += wstride) {
+    const Segment S = p.segs[sidx];
+    const int64_t b = S.row_b / p.M, row = S.row_b - b * p.M;
+    const int64_t base = S.start & ~(int64_t)31;
+    ring.reset(base);
+    const char* matb = (const char*)p.mat + b * p.N * row_bytes + lane_off;
+    Eng eng;
+    eng.init();
+    eng.accumulate(ring, (int)(S.start - base), (int)(S.end - base), matb, row_bytes, col_ok, lane, g, pol);
+    eng.reduce_groups();
+    if (g == 0) {
+      if (S.slot < 0) {
+        eng.store_row((T*)p.out + (b * p.M + row) * p.K + p.k0,
+                      p.arg_out ? p.arg_out + (b * p.M + row) * p.K + p.k0 : nullptr,
+                      S.end - S.start, p.E, col_ok, li, p.mean != 0);
+      } else {
+        float* pv = (float*)p.part_val + S.slot * p.K + p.k0;
+        int64_t* pa = Eng::ARG ? p.part_arg + S.slot * p.K + p.k0 : nullptr;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+          if (!col_ok[ch]) continue;
+          const int koff = (ch * LPR + li) * VEC;
+#pragma unroll
+          for (int i = 0; i < VEC; i++) {
+            pv[koff + i] = eng.acc[ch * VEC + i];
+            if (Eng::ARG) pa[koff + i] = eng.arg[ch * VEC + i] == 0x7fffffff ? p.E : (int64_t)eng.arg[ch * VEC + i];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// combine the partials of multi-segment rows, in segment order.
+template <typename T, int RED>
+__global__ void spmm_combine_kernel(const SpmmParams p, int kcols) {
+  constexpr bool ARG = (RED == R_MIN || RED == R_MAX);
+  const int64_t nlong = min((int64_t)p.counters[2], p.long_cap);
+  for (int64_t li = blockIdx.x; li < nlong; li += gridDim.x) {
+    const LongRow L = p.longs[li];
+    const int nseg = (int)(L.nseg_count >> 40);
+    const int64_t count = L.nseg_count & (((int64_t)1 << 40) - 1);
+    for (int k = threadIdx.x; k < kcols; k += blockDim.x) {
+      const int64_t kk = p.k0 + k;
+      if (kk >= p.K) break;
+      float a = ((const float*)p.part_val)[L.first_slot * p.K + kk];
+      int64_t ar = ARG ? p.part_arg[L.first_slot * p.K + kk] : 0;
+      for (int sgi = 1; sgi < nseg; sgi++) {
+        const float v = ((const float*)p.part_val)[(L.first_slot + sgi) * p.K + kk];
+        if (RED == R_SUM) a += v;
+        else {
+          const int64_t va = p.part_arg[(L.first_slot + sgi) * p.K + kk];
+          const bool better = (RED == R_MIN) ? (v < a) : (v > a);
+          if (better || (v == a && va < ar)) { a = v; ar = va; }
+        }
+      }
+      if (RED == R_SUM && p.mean) a = a / (float)(count > 0 ? count : 1);
+      ((T*)p.out)[L.row_b * p.K + kk] = Traits<T>::from_acc(a);
+      if (ARG) p.arg_out[L.row_b * p.K + kk] = ar;
+    }
+  }
+}
+
+// ---- generic fallback: warp per (b,row), lane per column, sequential nnz walk -------------------
+template <typename T, int RED>
+__global__ void __launch_bounds__(256)
+spmm_generic_kernel(const int64_t* __restrict__ rowptr, const int64_t* __restrict__ col,
+                    const T* __restrict__ value, const T* __restrict__ mat, T* __restrict__ out,
+                    int64_t* __restrict__ arg_out, int64_t B, int64_t M, int64_t N, int64_t K,
+                    int64_t E, bool mean) {
+  const bool HV = value != nullptr;
+  using acc_t = typename Traits<T>::acc_t;
+  constexpr bool ARG = (RED == R_MIN || RED == R_MAX);
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = wid; i < B * M; i += nw) {
+    const int64_t b = i / M, m = i - b * M;
+    const int64_t rs = rowptr[m], re = rowptr[m + 1];
+    const T* matb = mat + b * N * K;
+    for (int64_t k = lane; k < K; k += 32) {
+      acc_t a;
+      if (RED == R_MIN) a = Traits<T>::to_acc(Traits<T>::highest());
+      else if (RED == R_MAX) a = Traits<T>::to_acc(Traits<T>::lowest());
+      else a = (acc_t)0;
+      int64_t ar = E;
+      for (int64_t e = rs; e < re; e++) {
+        const int64_t c = col[e];
+        const acc_t mv = Traits<T>::to_acc(matb[c * K + k]);
+        acc_t pr;
+        if (HV) {
+          const acc_t vv = Traits<T>::to_acc(value[e]);
+          if constexpr (std::is_same<acc_t, float>::value) pr = __fmul_rn(vv, mv);
+          else if constexpr (std::is_same<acc_t, double>::value) pr = __dmul_rn(vv, mv);
+          else pr = (acc_t)(vv * mv);
+        } else {
+          pr = mv;
+        }
+        if (RED == R_SUM) {
+          if constexpr (std::is_same<acc_t, float>::value) a = __fadd_rn(a, pr);
+          else if constexpr (std::is_same<acc_t, double>::value) a = __dadd_rn(a, pr);
+          else a = (acc_t)(a + pr);
+        } else {
+          if constexpr (is_float16<T>::value) pr = Traits<T>::to_acc(Traits<T>::from_acc(pr));
+          const bool better = (RED == R_MIN) ? (pr < a) : (pr > a);
+          if (better) { a = pr; ar = e; }
+        }
+      }
+      const int64_t cnt = re - rs;
+      if (RED == R_SUM && mean) a = a / (acc_t)(cnt > 0 ? cnt : 1);
+      if (ARG && cnt == 0) a = (acc_t)0;
+      out[i * K + k] = Traits<T>::from_acc(a);
+      if (ARG) arg_out[i * K + k] = cnt > 0 ? ar : E;
+    }
+  }
+}
+
+// ---- dispatch ------------------------------------------------------------------------------------
+struct WsLayout {
+  size_t counters, segs, longs, part_val, part_arg, total;
+  int64_t seg_cap, long_cap, slot_cap;
+};
+static WsLayout ws_layout(int64_t B, int64_t K, int64_t E, bool arg) {
+  WsLayout L;
+  const int64_t EB = E * (B > 0 ? B : 1);
+  L.seg_cap = EB / 32 + EB / 128 + 64;
+  L.long_cap = EB / kLongT + 64;
+  L.slot_cap = EB / 128 + 64;
+  size_t off = 0;
+  L.counters = off; off += 256;
+  L.segs = off; off += align_up((size_t)L.seg_cap * sizeof(Segment), 256);
+  L.longs = off; off += align_up((size_t)L.long_cap * sizeof(LongRow), 256);
+  L.part_val = off; off += align_up((size_t)L.slot_cap * (size_t)K * sizeof(float), 256);
+  L.part_arg = off; off += arg ? align_up((size_t)L.slot_cap * (size_t)K * sizeof(int64_t), 256) : 0;
+  L.total = off;
+  return L;
+}
+
+static bool vec_eligible(int dtype, int64_t K, int64_t E, int64_t N, const void* value,
+                         const void* mat, const void* out, const void* col, const void* arg_out) {
+  if (dtype != TSB200_F32 && dtype != TSB200_F16 && dtype != TSB200_BF16) return false;
+  const size_t es = dtype_size(dtype);
+  if ((K * es) % 16 != 0) return false;
+  if (E >= ((int64_t)1 << 31) - 64) return false;
+  if (((uintptr_t)mat & 15) || ((uintptr_t)out & 15) || ((uintptr_t)col & 7)) return false;
+  if (value && ((uintptr_t)value & 3)) return false;
+  if (arg_out && ((uintptr_t)arg_out & 15)) return false;
+  (void)N;
+  return true;
+}
+
+static int grid_for(const void* kernel, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  int dev = 0, sms = kNumSMs;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return per_sm * sms;
+}
+
+template <typename T, int RED, int LPR, int CH, int U>
+static int launch_vec(SpmmParams p, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  constexpr int kcols = LPR * CH * VEC;
+  auto* kmain = spmm_vec_kernel<T, RED, LPR, CH, U>;
+  auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, U>;
+  static int grid_main = 0, grid_seg = 0;  // per-instantiation cache
+  if (!grid_main) grid_main = grid_for((const void*)kmain, kWarpsPerCta * 32);
+  if (!grid_seg) grid_seg = grid_for((const void*)kseg, kWarpsPerCta * 32);
+  const int64_t n_items = ((p.M + 31) >> 5) * p.B;
+  for (int k0 = 0; k0 < p.K; k0 += kcols) {
+    p.k0 = k0;
+    TSB_CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));
+    const int gm = (int)min((int64_t)grid_main, (n_items + kWarpsPerCta - 1) / kWarpsPerCta);
+    kmain<<<gm, kWarpsPerCta * 32, 0, st>>>(p);
+    TSB_LAUNCH_CHECK();
+    kseg<<<grid_seg, kWarpsPerCta * 32, 0, st>>>(p);
+    TSB_LAUNCH_CHECK();
+    spmm_combine_kernel<T, RED><<<kNumSMs * 2, 128, 0, st>>>(p, kcols);
+    TSB_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+template <typename T, int RED> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t vecs = p.K / VEC;  // 16-byte vectors per dense row
+  if (vecs <= 1) return launch_vec<T, RED, 1, 1, 1>(p, st);
+  if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4>(p, st);
+  if (vecs <= 8) return launch_vec<T, RED, 8, 1, 4>(p, st);
+  if (vecs <= 16) return launch_vec<T, RED, 16, 1, 8>(p, st);
+  if (vecs <= 32) return launch_vec<T, RED, 32, 1, 8>(p, st);
+  if (vecs <= 64) return launch_vec<T, RED, 32, 2, 4>(p, st);
+  return launch_vec<T, RED, 32, 4, 2>(p, st);  // column-tiled beyond 128 vectors
+}
+
+template <typename T> static int dispatch_red_vec(SpmmParams p, int reduce, cudaStream_t st) {
+  p.mean = (reduce == TSB200_MEAN);
+  switch (reduce) {
+    case TSB200_SUM:
+    case TSB200_MEAN: return dispatch_shape<T, R_SUM>(p, st);
+    case TSB200_MIN: return dispatch_shape<T, R_MIN>(p, st);
+    case TSB200_MAX: return dispatch_shape<T, R_MAX>(p, st);
+  }
+  return TSB200_ERR_INVALID_ARG;
+}
+
+template <typename T, int RED>
+static int launch_generic(const int64_t* rowptr, const int64_t* col, const void* value, const void* mat,
+                          void* out, int64_t* arg_out, int64_t B, int64_t M, int64_t N, int64_t K,
+                          int64_t E, bool mean, cudaStream_t st) {
+  const int64_t warps = B * M;
+  int64_t blocks = (warps + 7) / 8;
+  if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
+  if (blocks < 1) blocks = 1;
+  spmm_generic_kernel<T, RED><<<(int)blocks, 256, 0, st>>>(rowptr, col, (const T*)value, (const T*)mat,
+                                                           (T*)out, arg_out, B, M, N, K, E, mean);
+  TSB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tsb
+
+using namespace tsb;
+
+extern "C" size_t tsb200_spmm_fw_workspace_bytes(int64_t B, int64_t M, int64_t K, int64_t E, int dtype,
+                                                 int reduce) {
+  (void)M;
+  if (dtype != TSB200_F32 && dtype != TSB200_F16 && dtype != TSB200_BF16) return 0;
+  if (B <= 0 || K <= 0 || E <= 0) return 0;
+  return ws_layout(B, K, E, reduce == TSB200_MIN || reduce == TSB200_MAX).total;
+}
+
+extern "C" int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const void* value, const void* mat,
+                              void* out, int64_t* arg_out, int64_t B, int64_t M, int64_t N, int64_t K,
+                              int64_t E, int dtype, int reduce, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  if (B < 0 || M < 0 || N < 0 || K < 0 || E < 0) return TSB200_ERR_INVALID_ARG;
+  if (reduce < TSB200_SUM || reduce > TSB200_MAX) return TSB200_ERR_INVALID_ARG;
+  if (dtype_size(dtype) == 0) return TSB200_ERR_INVALID_ARG;
+  const bool arg = (reduce == TSB200_MIN || reduce == TSB200_MAX);
+  if (B * M * K == 0) return 0;  // nothing to write
+  if (!rowptr || !out || (arg && !arg_out)) return TSB200_ERR_INVALID_ARG;
+  if (E > 0 && (!col || !mat)) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  if (E > 0 && vec_eligible(dtype, K, E, N, value, mat, out, col, arg_out)) {
+    const WsLayout L = ws_layout(B, K, E, arg);
+    if (!workspace || workspace_bytes < L.total) return TSB200_ERR_WORKSPACE;
+    if ((uintptr_t)workspace & 255) return TSB200_ERR_INVALID_ARG;
+    char* ws = (char*)workspace;
+    SpmmParams p;
+    p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = arg_out;
+    p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0;
+    p.counters = (unsigned int*)(ws + L.counters);
+    p.segs = (Segment*)(ws + L.segs);
+    p.longs = (LongRow*)(ws + L.longs);
+    p.part_val = ws + L.part_val;
+    p.part_arg = arg ? (int64_t*)(ws + L.part_arg) : nullptr;
+    p.seg_cap = L.seg_cap; p.long_cap = L.long_cap; p.slot_cap = L.slot_cap;
+    switch (dtype) {
+      case TSB200_F32: return dispatch_red_vec<float>(p, reduce, st);
+      case TSB200_F16: return dispatch_red_vec<__half>(p, reduce, st);
+      case TSB200_BF16: return dispatch_red_vec<__nv_bfloat16>(p, reduce, st);
+    }
+  }
+
+  return dispatch_dtype(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    switch (reduce) {
+      case TSB200_SUM: return launch_generic<T, R_SUM>(rowptr, col, value, mat, out, arg_out, B, M, N, K, E, false, st);
+      case TSB200_MEAN: return launch_generic<T, R_SUM>(rowptr, col, value, mat, out, arg_out, B, M, N, K, E, true, st);
+      case TSB200_MIN: return launch_generic<T, R_MIN>(rowptr, col, value, mat, out, arg_out, B, M, N, K, E, false, st);
+      case TSB200_MAX: return launch_generic<T, R_MAX>(rowptr, col, value, mat, out, arg_out, B, M, N, K, E, false, st);
+    }
+    return TSB200_ERR_INVALID_ARG;
+  });
+}

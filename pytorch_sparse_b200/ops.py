@@ -1,0 +1,486 @@
+"""Tensor-level operators over the libtsb200 C-ABI.
+
+This module is the Python mirror of the reference's native operator layer
+(`torch.ops.torch_sparse.*`, csrc/spmm.cpp:305-348, csrc/convert.cpp:22-48): same names, argument
+meaning, optional-argument rules and error behaviour, with every computation done by the CUDA
+library. All functions require CUDA tensors and raise a RuntimeError for CPU tensors (like the
+reference's CHECK_CUDA, csrc/cuda/utils.cuh:5-6) — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import check, lib
+
+_DTYPES = {
+    torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.bfloat16: 3,
+    torch.int32: 4, torch.int64: 5, torch.int16: 6, torch.int8: 7, torch.uint8: 8,
+}
+_REDUCE = {"sum": 0, "add": 0, "mean": 1, "min": 2, "max": 3}
+
+
+def _dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _DTYPES[dtype]
+    except KeyError:
+        raise RuntimeError(f'"spmm" not implemented for \'{dtype}\'') from None
+
+
+def _reduce_code(reduce: str) -> int:
+    try:
+        return _REDUCE[reduce]
+    except KeyError:
+        raise ValueError(f"unknown reduce '{reduce}'") from None
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device: torch.device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_cuda(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be CUDA tensor")
+
+
+def _check_input(cond: bool) -> None:
+    if not cond:
+        raise RuntimeError("Input mismatch")
+
+
+def _workspace(nbytes: int, device: torch.device) -> Optional[Tensor]:
+    if nbytes <= 0:
+        return None
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def _i64(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.int64:
+        raise RuntimeError(f"{name} must be int64")
+    return t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# SpMM forward / value gradient / fused min-max backward
+# --------------------------------------------------------------------------------------------------
+def spmm_fw(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor,
+            reduce: str) -> Tuple[Tensor, Optional[Tensor]]:
+    """`spmm_fw(rowptr, col, optional_value, mat, reduce) -> (out, arg_out?)`
+    (csrc/spmm.cpp:22-35; checks follow csrc/cuda/spmm_cuda.cu:97-110)."""
+    _check_cuda(rowptr, "rowptr")
+    _check_cuda(col, "col")
+    if value is not None:
+        _check_cuda(value, "optional_value.value()")
+    _check_cuda(mat, "mat")
+    _check_input(rowptr.dim() == 1)
+    _check_input(col.dim() == 1)
+    if value is not None:
+        _check_input(value.dim() == 1)
+        _check_input(value.size(0) == col.size(0))
+        if value.dtype != mat.dtype:
+            raise RuntimeError(f"expected value of dtype {mat.dtype} but got {value.dtype}")
+        value = value.contiguous()
+    _check_input(mat.dim() >= 2)
+    red = _reduce_code(reduce)
+    rowptr = _i64(rowptr, "rowptr")
+    col = _i64(col, "col")
+    mat = mat.contiguous()
+    dt = _dtype_code(mat.dtype)
+
+    M = rowptr.numel() - 1
+    N, K = mat.size(-2), mat.size(-1)
+    B = mat.numel() // (N * K) if N * K > 0 else int(torch.Size(mat.shape[:-2]).numel())
+    E = col.numel()
+    sizes = list(mat.shape)
+    sizes[-2] = M
+    dev = mat.device
+    out = torch.empty(sizes, dtype=mat.dtype, device=dev)
+    arg_out = torch.empty(sizes, dtype=torch.int64, device=dev) if red >= 2 else None
+    if out.numel() == 0:
+        return out, arg_out
+    if E == 0:
+        out.zero_()
+        if arg_out is not None:
+            arg_out.fill_(0)
+        return out, arg_out
+    with torch.cuda.device(dev):
+        nws = lib.tsb200_spmm_fw_workspace_bytes(B, M, K, E, dt, red)
+        ws = _workspace(nws, dev)
+        check(lib.tsb200_spmm_fw(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(arg_out),
+                                 B, M, N, K, E, dt, red, _p(ws), nws, _stream(dev)), "tsb200_spmm_fw")
+    return out, arg_out
+
+
+def spmm_value_bw(row: Tensor, rowptr: Tensor, col: Tensor, mat: Tensor, grad: Tensor,
+                  reduce: str) -> Tensor:
+    """`spmm_value_bw(row, rowptr, col, mat, grad, reduce)` (csrc/spmm.cpp:37-49)."""
+    for t, n in ((row, "row"), (rowptr, "rowptr"), (col, "col"), (mat, "mat"), (grad, "grad")):
+        _check_cuda(t, n)
+    red = _reduce_code(reduce)
+    mat = mat.contiguous()
+    grad = grad.contiguous()
+    if grad.dtype != mat.dtype:
+        grad = grad.to(mat.dtype)
+    row, rowptr, col = _i64(row, "row"), _i64(rowptr, "rowptr"), _i64(col, "col")
+    M, N, K = grad.size(-2), mat.size(-2), mat.size(-1)
+    E = row.numel()
+    B = mat.numel() // (N * K) if N * K > 0 else 0
+    dev = mat.device
+    out = torch.zeros(E, dtype=grad.dtype, device=dev)
+    if E == 0 or B * K == 0:
+        return out
+    with torch.cuda.device(dev):
+        check(lib.tsb200_spmm_value_bw(_p(row), _p(rowptr), _p(col), _p(mat), _p(grad), _p(out),
+                                       B, M, N, K, E, _dtype_code(mat.dtype), red, _stream(dev)),
+              "tsb200_spmm_value_bw")
+    return out
+
+
+def spmm_minmax_bw(col: Tensor, value: Optional[Tensor], mat: Tensor, grad_out: Tensor, arg_out: Tensor,
+                   need_value: bool, need_mat: bool) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """Fused backward of spmm_min / spmm_max (replaces csrc/spmm.cpp:204-242, 264-302)."""
+    for t, n in ((col, "col"), (mat, "mat"), (grad_out, "grad_out"), (arg_out, "arg_out")):
+        _check_cuda(t, n)
+    if not mat.dtype.is_floating_point:
+        raise RuntimeError("spmm_min/max backward needs a floating point dtype")
+    mat = mat.contiguous()
+    grad_out = grad_out.contiguous().to(mat.dtype)
+    arg_out = arg_out.contiguous()
+    col = _i64(col, "col")
+    if value is not None:
+        value = value.contiguous()
+    N, K = mat.size(-2), mat.size(-1)
+    M = grad_out.size(-2)
+    E = col.numel()
+    B = mat.numel() // (N * K) if N * K > 0 else 0
+    dev = mat.device
+    acc = torch.float64 if mat.dtype == torch.float64 else torch.float32
+    gv = torch.zeros(E, dtype=acc, device=dev) if need_value else None
+    gm = torch.zeros(mat.shape, dtype=acc, device=dev) if need_mat else None
+    if E > 0 and B * M * K > 0 and (need_value or need_mat):
+        with torch.cuda.device(dev):
+            check(lib.tsb200_spmm_minmax_bw(_p(col), _p(value), _p(mat), _p(grad_out), _p(arg_out), _p(gv),
+                                            _p(gm), B, M, N, K, E, _dtype_code(mat.dtype), _stream(dev)),
+                  "tsb200_spmm_minmax_bw")
+    if gv is not None and gv.dtype != mat.dtype:
+        gv = gv.to(mat.dtype)
+    if gm is not None and gm.dtype != mat.dtype:
+        gm = gm.to(mat.dtype)
+    return gv, gm
+
+
+# --------------------------------------------------------------------------------------------------
+# format kernels
+# --------------------------------------------------------------------------------------------------
+def ind2ptr(ind: Tensor, M: int) -> Tensor:
+    """`torch.ops.torch_sparse.ind2ptr(ind, M)` (csrc/convert.cpp:22-33)."""
+    _check_cuda(ind, "ind")
+    ind = _i64(ind, "ind")
+    out = torch.empty(M + 1, dtype=torch.int64, device=ind.device)
+    with torch.cuda.device(ind.device):
+        check(lib.tsb200_ind2ptr(_p(ind), ind.numel(), M, _p(out), _stream(ind.device)), "tsb200_ind2ptr")
+    return out
+
+
+def ptr2ind(ptr: Tensor, E: int) -> Tensor:
+    """`torch.ops.torch_sparse.ptr2ind(ptr, E)` (csrc/convert.cpp:35-45)."""
+    _check_cuda(ptr, "ptr")
+    ptr = _i64(ptr, "ptr")
+    out = torch.empty(E, dtype=torch.int64, device=ptr.device)
+    with torch.cuda.device(ptr.device):
+        check(lib.tsb200_ptr2ind(_p(ptr), ptr.numel() - 1, E, _p(out), _stream(ptr.device)), "tsb200_ptr2ind")
+    return out
+
+
+def csr2csc(row: Tensor, col: Tensor, M: int, N: int, want_colptr: bool = True,
+            want_row_csc: bool = False) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
+    """csr2csc permutation (+ colptr, + row[csr2csc]) of a row-major sorted COO
+    (torch_sparse/storage.py:369-385, 407-416)."""
+    _check_cuda(row, "row")
+    _check_cuda(col, "col")
+    row, col = _i64(row, "row"), _i64(col, "col")
+    E, dev = col.numel(), col.device
+    perm = torch.empty(E, dtype=torch.int64, device=dev)
+    colptr = torch.empty(N + 1, dtype=torch.int64, device=dev) if want_colptr else None
+    row_csc = torch.empty(E, dtype=torch.int64, device=dev) if want_row_csc else None
+    with torch.cuda.device(dev):
+        nws = lib.tsb200_csr2csc_workspace_bytes(E, M, N)
+        ws = _workspace(nws, dev)
+        check(lib.tsb200_csr2csc(_p(row), _p(col), E, M, N, _p(perm), _p(colptr), _p(row_csc), _p(ws), nws,
+                                 _stream(dev)), "tsb200_csr2csc")
+    return perm, colptr, row_csc
+
+
+class _PinnedScalar:
+    """One pinned int64 per device-side count read back from the GPU (E', nnz(C))."""
+
+    def __init__(self):
+        self.t = torch.zeros(1, dtype=torch.int64).pin_memory()
+
+    def ptr(self):
+        return ctypes.c_void_p(self.t.data_ptr())
+
+
+def sort_perm(row: Tensor, col: Tensor, M: int, N: int) -> Optional[Tensor]:
+    """Stable permutation that sorts (row, col) row-major — the sort-on-construct of
+    SparseStorage (torch_sparse/storage.py:149-162). Returns None when the input is already
+    sorted (the reference skips the sort in that case too, storage.py:154)."""
+    _check_cuda(row, "row")
+    _check_cuda(col, "col")
+    row, col = _i64(row, "row"), _i64(col, "col")
+    E, dev = col.numel(), col.device
+    if E < 2:
+        return None
+    with torch.cuda.device(dev):
+        nws = lib.tsb200_coalesce_workspace_bytes(E, M, N)
+        ws = _workspace(nws, dev)
+        st = _stream(dev)
+        check(lib.tsb200_coalesce_sort(_p(row), _p(col), E, M, N, _p(ws), nws, None, st), "tsb200_coalesce_sort")
+        if int(ws[:4].view(torch.int32).item()) == 0:  # device flag "input was unsorted"
+            return None
+        perm = torch.empty(E, dtype=torch.int64, device=dev)
+        check(lib.tsb200_coalesce_perm(E, _p(perm), _p(ws), st), "tsb200_coalesce_perm")
+    return perm
+
+
+def coalesce(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int,
+             reduce: str = "add") -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+    """Sort by (row, col), merge duplicate entries, reduce their values
+    (torch_sparse/coalesce.py:5-25 -> torch_sparse/storage.py:149-162, 436-466)."""
+    _check_cuda(row, "row")
+    _check_cuda(col, "col")
+    row, col = _i64(row, "row"), _i64(col, "col")
+    red = _reduce_code(reduce)
+    E, dev = col.numel(), col.device
+    if value is not None:
+        _check_cuda(value, "value")
+        _check_input(value.size(0) == E)
+        value = value.contiguous()
+    if E == 0:
+        return row, col, value
+    with torch.cuda.device(dev):
+        nws = lib.tsb200_coalesce_workspace_bytes(E, M, N)
+        ws = _workspace(nws, dev)
+        st = _stream(dev)
+        pin = _PinnedScalar()
+        check(lib.tsb200_coalesce_sort(_p(row), _p(col), E, M, N, _p(ws), nws, pin.ptr(), st),
+              "tsb200_coalesce_sort")
+        torch.cuda.current_stream(dev).synchronize()
+        n_unique = int(pin.t.item())
+        row_out = torch.empty(n_unique, dtype=torch.int64, device=dev)
+        col_out = torch.empty(n_unique, dtype=torch.int64, device=dev)
+        value_out = None
+        D, dt = 1, 0
+        if value is not None:
+            D = value.numel() // E
+            dt = _dtype_code(value.dtype)
+            value_out = torch.empty((n_unique,) + tuple(value.shape[1:]), dtype=value.dtype, device=dev)
+        check(lib.tsb200_coalesce_emit(E, N, n_unique, _p(value), D, dt, red, _p(row_out), _p(col_out),
+                                       _p(value_out), None, _p(ws), st), "tsb200_coalesce_emit")
+    return row_out, col_out, value_out
+
+
+def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: Tensor, col_b: Tensor,
+           val_b: Optional[Tensor], M: int, Kd: int, N: int,
+           want_value: bool) -> Tuple[Tensor, Tensor, Tensor, Optional[Tensor]]:
+    """C = A @ B for CSR operands -> (rowptr_c, row_c, col_c, val_c?) sorted, unique, structural
+    (replaces torch.sparse.mm at torch_sparse/matmul.py:94-111)."""
+    for t, n in ((rowptr_a, "rowptrA"), (col_a, "colA"), (rowptr_b, "rowptrB"), (col_b, "colB")):
+        _check_cuda(t, n)
+    rowptr_a, col_a = _i64(rowptr_a, "rowptrA"), _i64(col_a, "colA")
+    rowptr_b, col_b = _i64(rowptr_b, "rowptrB"), _i64(col_b, "colB")
+    dev = col_a.device
+    dtype = None
+    if want_value:
+        dtype = val_a.dtype if val_a is not None else (val_b.dtype if val_b is not None else torch.float32)
+        if val_a is not None and val_b is not None and val_a.dtype != val_b.dtype:
+            raise RuntimeError("spspmm: value dtypes of both operands must match")
+        if dtype not in (torch.float32, torch.float64):
+            # torch.sparse.mm: '"sparse_matmul" not implemented' for Half/BFloat16/integers
+            raise RuntimeError(f'"sparse_matmul" not implemented for \'{dtype}\'')
+        val_a = None if val_a is None else val_a.contiguous()
+        val_b = None if val_b is None else val_b.contiguous()
+    else:
+        val_a = val_b = None
+    nnz_a, nnz_b = col_a.numel(), col_b.numel()
+    rowptr_c = torch.empty(M + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        nws = lib.tsb200_spspmm_workspace_bytes(M, Kd, N, nnz_a, nnz_b)
+        ws = _workspace(nws, dev)
+        st = _stream(dev)
+        pin = _PinnedScalar()
+        check(lib.tsb200_spspmm_symbolic(_p(rowptr_a), _p(col_a), _p(rowptr_b), _p(col_b), M, Kd, N, nnz_a,
+                                         nnz_b, _p(rowptr_c), _p(ws), nws, pin.ptr(), st),
+              "tsb200_spspmm_symbolic")
+        torch.cuda.current_stream(dev).synchronize()
+        nnz_c = int(pin.t.item())
+        row_c = torch.empty(nnz_c, dtype=torch.int64, device=dev)
+        col_c = torch.empty(nnz_c, dtype=torch.int64, device=dev)
+        val_c = torch.empty(nnz_c, dtype=dtype, device=dev) if want_value else None
+        if nnz_c > 0:
+            check(lib.tsb200_spspmm_numeric(_p(rowptr_a), _p(col_a), _p(val_a), _p(rowptr_b), _p(col_b),
+                                            _p(val_b), M, Kd, N, nnz_a, nnz_b, _p(rowptr_c), _p(row_c),
+                                            _p(col_c), _p(val_c), _dtype_code(dtype) if want_value else 0,
+                                            _p(ws), nws, st), "tsb200_spspmm_numeric")
+    return rowptr_c, row_c, col_c, val_c
+
+
+def spmm_fw_host(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor,
+                 reduce: str = "sum") -> Tuple[Tensor, Optional[Tensor]]:
+    """Host-buffer SpMM: CPU tensors in, CPU tensors out, H2D/D2H inside (tsb200_spmm_fw_host)."""
+    for t, n in ((rowptr, "rowptr"), (col, "col"), (mat, "mat")):
+        if t.is_cuda:
+            raise RuntimeError(f"{n} must be CPU tensor")
+    red = _reduce_code(reduce)
+    rowptr, col, mat = _i64(rowptr, "rowptr"), _i64(col, "col"), mat.contiguous()
+    if value is not None:
+        value = value.to(mat.dtype).contiguous()
+    M = rowptr.numel() - 1
+    N, K = mat.size(-2), mat.size(-1)
+    B = mat.numel() // (N * K) if N * K > 0 else 0
+    sizes = list(mat.shape)
+    sizes[-2] = M
+    pin = mat.is_pinned()
+    out = torch.empty(sizes, dtype=mat.dtype, pin_memory=pin)
+    arg_out = torch.empty(sizes, dtype=torch.int64, pin_memory=pin) if red >= 2 else None
+    check(lib.tsb200_spmm_fw_host(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(arg_out), B, M, N, K,
+                                  col.numel(), _dtype_code(mat.dtype), red), "tsb200_spmm_fw_host")
+    return out, arg_out
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd Functions mirroring SPMMSum / SPMMMean / SPMMMin / SPMMMax (csrc/spmm.cpp:55-303)
+# --------------------------------------------------------------------------------------------------
+def _assert_present(t: Optional[Tensor], name: str) -> None:
+    if t is None:
+        raise RuntimeError(f"Argument `{name}` is missing")
+
+
+class SPMMSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, row, rowptr, col, value, colptr, csr2csc, mat):
+        has_value = value is not None
+        need_value = has_value and ctx.needs_input_grad[3]
+        need_mat = ctx.needs_input_grad[6]
+        if need_value:
+            _assert_present(row, "row")
+        if need_mat:
+            _assert_present(row, "row")
+            _assert_present(colptr, "colptr")
+            _assert_present(csr2csc, "csr2csc")
+        out, _ = spmm_fw(rowptr, col, value, mat, "sum")
+        ctx.has_value = has_value
+        ctx.save_for_backward(row, rowptr, col, value, colptr, csr2csc, mat)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        row, rowptr, col, value, colptr, csr2csc, mat = ctx.saved_tensors
+        grad_value = grad_mat = None
+        if ctx.has_value and ctx.needs_input_grad[3]:
+            grad_value = spmm_value_bw(row, rowptr, col, mat, grad_out, "sum")
+        if ctx.needs_input_grad[6]:
+            # grad_mat = A^T @ grad_out as a CSR SpMM on the CSC view (csrc/spmm.cpp:100-108)
+            v = value.index_select(0, csr2csc) if ctx.has_value else None
+            grad_mat, _ = spmm_fw(colptr, row.index_select(0, csr2csc), v, grad_out, "sum")
+        return None, None, None, grad_value, None, None, grad_mat
+
+
+class SPMMMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, row, rowptr, col, value, rowcount, colptr, csr2csc, mat):
+        has_value = value is not None
+        if has_value and ctx.needs_input_grad[3]:
+            _assert_present(row, "row")
+        if ctx.needs_input_grad[7]:
+            _assert_present(row, "row")
+            _assert_present(rowcount, "rowcount")
+            _assert_present(colptr, "colptr")
+            _assert_present(csr2csc, "csr2csc")
+        out, _ = spmm_fw(rowptr, col, value, mat, "mean")
+        ctx.has_value = has_value
+        ctx.save_for_backward(row, rowptr, col, value, rowcount, colptr, csr2csc, mat)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        row, rowptr, col, value, rowcount, colptr, csr2csc, mat = ctx.saved_tensors
+        grad_value = grad_mat = None
+        if ctx.has_value and ctx.needs_input_grad[3]:
+            grad_value = spmm_value_bw(row, rowptr, col, mat, grad_out, "mean")
+        if ctx.needs_input_grad[7]:
+            # per-nnz weight value/count(row) (or 1/count) in CSC order (csrc/spmm.cpp:166-177)
+            row_csc = row.index_select(0, csr2csc)
+            cnt = rowcount.index_select(0, row_csc).to(mat.dtype).clamp_(min=1)
+            w = value.index_select(0, csr2csc).div(cnt) if ctx.has_value else cnt.reciprocal_()
+            grad_mat, _ = spmm_fw(colptr, row_csc, w, grad_out, "sum")
+        return None, None, None, grad_value, None, None, None, grad_mat
+
+
+def _minmax_forward(ctx, reduce, rowptr, col, value, mat):
+    out, arg_out = spmm_fw(rowptr, col, value, mat, reduce)
+    ctx.has_value = value is not None
+    ctx.save_for_backward(col, value, mat, arg_out)
+    ctx.mark_non_differentiable(arg_out)
+    return out, arg_out
+
+
+def _minmax_backward(ctx, grad_out):
+    col, value, mat, arg_out = ctx.saved_tensors
+    need_value = ctx.has_value and ctx.needs_input_grad[2]
+    need_mat = ctx.needs_input_grad[3]
+    grad_value, grad_mat = spmm_minmax_bw(col, value, mat, grad_out, arg_out, need_value, need_mat)
+    return None, None, grad_value, grad_mat
+
+
+class SPMMMin(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rowptr, col, value, mat):
+        return _minmax_forward(ctx, "min", rowptr, col, value, mat)
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_arg):
+        return _minmax_backward(ctx, grad_out)
+
+
+class SPMMMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rowptr, col, value, mat):
+        return _minmax_forward(ctx, "max", rowptr, col, value, mat)
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_arg):
+        return _minmax_backward(ctx, grad_out)
+
+
+# Exported operators: same signatures as torch.ops.torch_sparse.spmm_{sum,mean,min,max}
+# (csrc/spmm.cpp:305-342).
+def spmm_sum(row: Optional[Tensor], rowptr: Tensor, col: Tensor, value: Optional[Tensor],
+             colptr: Optional[Tensor], csr2csc: Optional[Tensor], mat: Tensor) -> Tensor:
+    return SPMMSum.apply(row, rowptr, col, value, colptr, csr2csc, mat)
+
+
+def spmm_mean(row: Optional[Tensor], rowptr: Tensor, col: Tensor, value: Optional[Tensor],
+              rowcount: Optional[Tensor], colptr: Optional[Tensor], csr2csc: Optional[Tensor],
+              mat: Tensor) -> Tensor:
+    return SPMMMean.apply(row, rowptr, col, value, rowcount, colptr, csr2csc, mat)
+
+
+def spmm_min(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor) -> Tuple[Tensor, Tensor]:
+    return SPMMMin.apply(rowptr, col, value, mat)
+
+
+def spmm_max(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor) -> Tuple[Tensor, Tensor]:
+    return SPMMMax.apply(rowptr, col, value, mat)
+
+
+def cuda_version() -> int:
+    return _lib.lib.tsb200_version()

@@ -1,0 +1,83 @@
+"""Drop-in surface: functional spmm (test/test_spmm.py), operator registry, argument rules and
+error behaviour of the reference's operator layer (csrc/spmm.cpp:64-72)."""
+import pytest
+import torch
+
+import pytorch_sparse_b200 as ts
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("dtype", [torch.half, torch.float, torch.double, torch.int, torch.long, torch.bfloat16])
+def test_functional_spmm_known_answer(dtype):
+    """test/test_spmm.py:10-19"""
+    row = torch.tensor([0, 0, 1, 2, 2], device=DEV)
+    col = torch.tensor([0, 2, 1, 0, 1], device=DEV)
+    index = torch.stack([row, col], dim=0)
+    value = torch.tensor([1, 2, 4, 1, 3], dtype=dtype, device=DEV)
+    x = torch.tensor([[1, 4], [2, 5], [3, 6]], dtype=dtype, device=DEV)
+    out = ts.spmm(index, value, 3, 3, x)
+    assert out.tolist() == [[7, 16], [8, 20], [7, 19]]
+
+
+def test_functional_spmm_unsorted_duplicates_and_grad():
+    g = torch.Generator().manual_seed(0)
+    E, M, N, K = 500, 40, 30, 16
+    row = torch.randint(M, (E,), generator=g).to(DEV)
+    col = torch.randint(N, (E,), generator=g).to(DEV)
+    value = torch.randn(E, generator=g, dtype=torch.float64).to(DEV).requires_grad_()
+    x = torch.randn(N, K, generator=g, dtype=torch.float64).to(DEV).requires_grad_()
+    out = ts.spmm(torch.stack([row, col]), value, M, N, x)
+    dense = torch.zeros(M, N, dtype=torch.float64, device=DEV).index_put((row, col), value.detach(), accumulate=True)
+    assert torch.allclose(out, dense @ x.detach(), atol=1e-10)
+    go = torch.randn(M, K, generator=g, dtype=torch.float64).to(DEV)
+    out.backward(go)
+    assert torch.allclose(x.grad, dense.t() @ go, atol=1e-10)
+    exp_gv = (go[row] * x.detach()[col]).sum(-1)
+    assert torch.allclose(value.grad, exp_gv, atol=1e-10)
+
+
+def test_registered_ops_and_optional_argument_rules():
+    src = ts.SparseTensor.from_dense(torch.eye(4, device=DEV))
+    rowptr, col, value = src.csr()
+    x = torch.randn(4, 8, device=DEV)
+    out = torch.ops.tsb200.spmm_sum(None, rowptr, col, value, None, None, x)
+    assert torch.allclose(out, x)
+    if ts.torch_ops.REGISTERED.get("torch_sparse"):
+        out = torch.ops.torch_sparse.spmm_sum(None, rowptr, col, value, None, None, x)
+        assert torch.allclose(out, x)
+        o, a = torch.ops.torch_sparse.spmm_max(rowptr, col, value, x)
+        assert torch.allclose(o, x) and a.dtype == torch.long
+    xg = x.clone().requires_grad_()
+    with pytest.raises(RuntimeError, match="Argument `row` is missing"):
+        torch.ops.tsb200.spmm_sum(None, rowptr, col, value, None, None, xg)
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        torch.ops.tsb200.spmm_sum(None, rowptr.cpu(), col.cpu(), value.cpu(), None, None, x.cpu())
+    with pytest.raises(ValueError):
+        ts.matmul(src, x, "prod")
+
+
+def test_cpu_built_tensor_moves_to_gpu():
+    row = torch.tensor([1, 0, 1, 0])
+    col = torch.tensor([0, 1, 1, 0])
+    val = torch.tensor([1., 2., 3., 4.])
+    a = ts.SparseTensor(row=row, col=col, value=val, sparse_sizes=(2, 2)).cuda()
+    x = torch.eye(2, device=DEV)
+    assert (a @ x).tolist() == [[4., 2.], [1., 3.]]
+    assert (a.t() @ x).tolist() == [[4., 1.], [2., 3.]]
+
+
+def test_host_buffer_spmm(oracle):
+    from pytorch_sparse_b200 import ops
+    from util import random_csr
+    row, rowptr, col = random_csr(5000, 3000, 9, seed=4, power_law=True)
+    g = torch.Generator().manual_seed(1)
+    value = torch.randn(col.numel(), generator=g)
+    mat = torch.randn(3000, 32, generator=g)
+    for reduce in ("sum", "max"):
+        out, arg = ops.spmm_fw_host(rowptr, col, value, mat, reduce)
+        dout, darg = ops.spmm_fw(rowptr.to(DEV), col.to(DEV), value.to(DEV), mat.to(DEV), reduce)
+        assert torch.equal(out, dout.cpu())
+        if arg is not None:
+            assert torch.equal(arg, darg.cpu())

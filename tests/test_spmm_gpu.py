@@ -1,0 +1,227 @@
+"""GPU parity of the CSR SpMM forward/backward against the oracle (CPU restatement of
+csrc/cpu/spmm_cpu.cpp) — mirrors test/test_matmul.py::test_spmm of the reference."""
+from itertools import product
+
+import pytest
+import torch
+
+import pytorch_sparse_b200 as ts
+from pytorch_sparse_b200 import ops
+from util import fast_random_csr, random_csr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+REDUCES = ["sum", "mean", "min", "max"]
+# fp tolerances stated by BASELINE.json north_star: 1e-5 rel fp32, 1e-2 rel bf16 (fp16 ~ 2e-3)
+TOL = {torch.float32: 1e-5, torch.float64: 1e-12, torch.bfloat16: 1e-2, torch.float16: 2e-3}
+
+
+def _abs_bound(rowptr, col, value, mat):
+    """componentwise normaliser |A| @ |B| (SURVEY §8d parity checks), fp64 on CPU via the oracle."""
+    import oracle
+    v = None if value is None else value.double().abs()
+    out, _ = oracle.spmm(rowptr, col, v, mat.double().abs(), "sum")
+    return out
+
+
+def _check_forward(oracle, rowptr, col, value, mat, reduce):
+    out, arg = ops.spmm_fw(rowptr.to(DEV), col.to(DEV), None if value is None else value.to(DEV), mat.to(DEV), reduce)
+    # reference semantics in exact arithmetic: oracle in fp64 on the (upcast) inputs
+    ref64, arg64 = oracle.spmm(rowptr, col, None if value is None else value.double(), mat.double(), reduce)
+    tol = TOL[mat.dtype]
+    if mat.dtype.is_floating_point:
+        bound = _abs_bound(rowptr, col, value, mat).clamp_min(1e-30)
+        if reduce == "mean":
+            pass  # |mean| <= |sum| bound still valid
+        err = ((out.cpu().double() - ref64).abs() / bound).max().item() if out.numel() else 0.0
+        assert err <= tol, f"{reduce} {mat.dtype}: rel err {err:.3e} > {tol}"
+    else:
+        assert torch.equal(out.cpu(), ref64.to(mat.dtype))
+    if reduce in ("min", "max"):
+        # the reference compares products rounded to the storage dtype: oracle in the storage dtype
+        ref_t, arg_t = oracle.spmm(rowptr, col, value, mat, reduce)
+        assert torch.equal(arg.cpu(), arg_t), f"arg_out mismatch ({reduce}, {mat.dtype})"
+        assert torch.equal(out.cpu(), ref_t), f"min/max values must be bit-exact ({reduce}, {mat.dtype})"
+    return out, arg
+
+
+@pytest.mark.parametrize("dtype,reduce", product([torch.float32, torch.bfloat16, torch.float16, torch.float64,
+                                                  torch.int32, torch.int64], REDUCES))
+def test_reference_shape(oracle, dtype, reduce):
+    """10x8 with empty rows 2-3 / empty cols 2-3, other [2, 8, 2] — test/test_matmul.py:18-25."""
+    torch.manual_seed(1)
+    dense = torch.randn(10, 8)
+    dense[2:4, :] = 0
+    dense[:, 2:4] = 0
+    if not dtype.is_floating_point:
+        dense = (dense * 4).round()
+    src = ts.SparseTensor.from_dense(dense.to(dtype))
+    rowptr, col, value = src.csr()
+    other = torch.randn(2, 8, 2)
+    other = (other * 4).round().to(dtype) if not dtype.is_floating_point else other.to(dtype)
+    _check_forward(oracle, rowptr, col, value, other, reduce)
+    _check_forward(oracle, rowptr, col, None, other, reduce)
+
+
+SHAPES = [  # (M, N, K, avg_deg, power_law)
+    (300, 200, 128, 16, False),
+    (257, 300, 32, 5, False),
+    (100, 90, 256, 12, True),
+    (64, 50, 8, 3, False),
+    (50, 70, 520, 6, False),    # bf16: 65 vectors -> CH=4 tile path
+    (40, 60, 1100, 4, False),   # fp32: 275 vectors -> column-tiled launches
+    (33, 20, 7, 4, False),      # odd K -> generic kernel
+]
+
+
+@pytest.mark.parametrize("shape,dtype,reduce", product(SHAPES, [torch.float32, torch.bfloat16], REDUCES))
+def test_random_shapes(oracle, shape, dtype, reduce):
+    M, N, K, deg, pl = shape
+    row, rowptr, col = random_csr(M, N, deg, seed=M + K, power_law=pl, empty_rows=(0, M // 2, M - 1))
+    g = torch.Generator().manual_seed(7)
+    value = torch.randn(col.numel(), generator=g).to(dtype)
+    mat = torch.randn(N, K, generator=g).to(dtype)
+    _check_forward(oracle, rowptr, col, value, mat, reduce)
+
+
+@pytest.mark.parametrize("dtype,reduce", product([torch.float32, torch.bfloat16], REDUCES))
+def test_long_rows_and_budget(oracle, dtype, reduce):
+    """rows longer than the 256-nnz segment length (multi-segment combine), a row of exactly 256/257,
+    and a dense 32-row block that exceeds the 1024-nnz item budget (single-segment deferral)."""
+    M, N, K = 200, 1500, 64
+    long_rows = [(5, 1400), (6, 256), (7, 257), (100, 700)] + [(r, 60) for r in range(128, 160)]
+    row, rowptr, col = random_csr(M, N, 4, seed=3, empty_rows=(0, 8, 199), long_rows=long_rows)
+    g = torch.Generator().manual_seed(11)
+    value = torch.randn(col.numel(), generator=g).to(dtype)
+    mat = torch.randn(N, K, generator=g).to(dtype)
+    _check_forward(oracle, rowptr, col, value, mat, reduce)
+    _check_forward(oracle, rowptr, col, None, mat, reduce)
+
+
+def test_ties_keep_first(oracle):
+    """duplicate maxima: strict compare keeps the smallest nnz index (csrc/cpu/reducer.h:63-67)."""
+    rowptr = torch.tensor([0, 600, 600, 603])
+    col = torch.cat([torch.arange(600) % 7, torch.tensor([1, 1, 2])])
+    value = torch.ones(603)
+    mat = torch.ones(7, 16)
+    for reduce in ("min", "max"):
+        out, arg = _check_forward(oracle, rowptr, col, value, mat, reduce)
+        assert arg[0].eq(0).all() and arg[1].eq(603).all() and arg[2].eq(600).all()
+        assert out[1].eq(0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float64])
+@pytest.mark.parametrize("reduce", ["sum", "mean"])
+def test_value_bw(oracle, dtype, reduce):
+    for (M, N, K, B) in [(120, 90, 128, 1), (60, 40, 32, 2), (30, 20, 6, 3)]:
+        row, rowptr, col = random_csr(M, N, 6, seed=K, power_law=True, empty_rows=(1,))
+        g = torch.Generator().manual_seed(5)
+        mat = torch.randn(B, N, K, generator=g).to(dtype)
+        grad = torch.randn(B, M, K, generator=g).to(dtype)
+        out = ops.spmm_value_bw(row.to(DEV), rowptr.to(DEV), col.to(DEV), mat.to(DEV), grad.to(DEV), reduce)
+        ref = oracle.spmm_value_bw(row, rowptr, col, mat.double(), grad.double(), reduce)
+        bound = oracle.spmm_value_bw(row, rowptr, col, mat.double().abs(), grad.double().abs(), reduce)
+        err = ((out.cpu().double() - ref).abs() / bound.clamp_min(1e-30)).max().item()
+        assert err <= TOL[dtype], f"value_bw {dtype} {reduce}: {err:.3e}"
+
+
+@pytest.mark.parametrize("dtype,reduce", product([torch.float32, torch.float64, torch.bfloat16, torch.float16],
+                                                 ["sum", "add", "mean", "min", "max"]))
+def test_autograd_like_reference(oracle, dtype, reduce):
+    """forward + grad wrt value + grad wrt other through matmul(), as test/test_matmul.py:12-51,
+    expected values from dense autograd in fp64."""
+    torch.manual_seed(3)
+    dense = torch.randn(10, 8, dtype=torch.float64)
+    dense[2:4, :] = 0
+    dense[:, 2:4] = 0
+    src = ts.SparseTensor.from_dense(dense.to(dtype).to(DEV)).requires_grad_()
+    row, col, value = src.coo()
+    other = torch.randn(2, 8, 2, dtype=torch.float64).to(dtype).to(DEV).requires_grad_()
+
+    # expected: fp64 dense formulation of the same reduction
+    v64 = value.detach().double().cpu().requires_grad_()
+    o64 = other.detach().double().cpu().requires_grad_()
+    r, c = row.cpu(), col.cpu()
+    src_col = o64.index_select(-2, c) * v64.unsqueeze(-1)  # [2, E, 2]
+    M = 10
+    if reduce in ("sum", "add", "mean"):
+        exp = torch.zeros(2, M, 2, dtype=torch.float64).index_add(-2, r, src_col)
+        if reduce == "mean":
+            cnt = torch.bincount(r, minlength=M).clamp(min=1).view(1, M, 1)
+            exp = exp / cnt
+    else:
+        fill = float("inf") if reduce == "min" else float("-inf")
+        exp = torch.full((2, M, 2), fill, dtype=torch.float64)
+        idx = r.view(1, -1, 1).expand_as(src_col)
+        exp = exp.scatter_reduce(-2, idx, src_col, reduce="amin" if reduce == "min" else "amax", include_self=True)
+        exp = torch.where(torch.isinf(exp), torch.zeros_like(exp), exp)
+    grad_out = torch.randn(2, M, 2, dtype=torch.float64)
+    exp.backward(grad_out)
+
+    out = ts.matmul(src, other, reduce)
+    out.backward(grad_out.to(dtype).to(DEV))
+    atol = 1e-1 if dtype in (torch.float16, torch.bfloat16) else (1e-5 if dtype == torch.float32 else 1e-10)
+    assert torch.allclose(exp, out.detach().double().cpu(), atol=atol)
+    assert torch.allclose(v64.grad, value.grad.double().cpu(), atol=atol)
+    assert torch.allclose(o64.grad, other.grad.double().cpu(), atol=atol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_minmax_backward_vs_oracle(oracle, dtype):
+    M, N, K = 150, 120, 64
+    row, rowptr, col = random_csr(M, N, 8, seed=9, power_law=True, empty_rows=(3, 4))
+    g = torch.Generator().manual_seed(2)
+    value = torch.randn(col.numel(), generator=g).to(dtype)
+    mat = torch.randn(N, K, generator=g).to(dtype)
+    grad_out = torch.randn(M, K, generator=g).to(dtype)
+    for reduce in ("min", "max"):
+        _, arg = oracle.spmm(rowptr, col, value, mat, reduce)
+        gv, gm = ops.spmm_minmax_bw(col.to(DEV), value.to(DEV), mat.to(DEV), grad_out.to(DEV), arg.to(DEV), True, True)
+        rv, rm = oracle.spmm_minmax_bw(col, value.double(), mat.double(), grad_out.double(), arg)
+        tol = 1e-5 if dtype == torch.float32 else 2e-2
+        assert torch.allclose(gv.double().cpu(), rv, rtol=tol, atol=tol)
+        assert torch.allclose(gm.double().cpu(), rm, rtol=tol, atol=tol)
+
+
+def test_full_size_properties():
+    """BASELINE config 2 at full size (1M x 1M, ~16 nnz/row, F=128 bf16): size-independent properties —
+    linearity in the dense operand, row-sum identity with an all-ones operand, agreement of the
+    bf16 result with the fp32 kernel on the same (bf16-representable) inputs, and row-block
+    decomposition (SpMM of a row slice == slice of the SpMM)."""
+    M = N = 1_000_000
+    F = 128
+    row, rowptr, col = fast_random_csr(M, N, 16, seed=1, device=DEV)
+    E = col.numel()
+    g = torch.Generator(device=DEV).manual_seed(2)
+    value = (torch.rand(E, generator=g, device=DEV) + 0.5).bfloat16()
+    x = torch.randn(N, F, generator=g, device=DEV).bfloat16()
+    y, _ = ops.spmm_fw(rowptr, col, value, x, "sum")
+    y32, _ = ops.spmm_fw(rowptr, col, value.float(), x.float(), "sum")
+    absb, _ = ops.spmm_fw(rowptr, col, value.float().abs(), x.float().abs(), "sum")
+    err = ((y.float() - y32).abs() / absb.clamp_min(1e-20)).max().item()
+    assert err <= 1e-2, err
+    # all-ones operand: out[m, :] == sum of the row's values (exactly representable check in fp32)
+    ones = torch.ones(N, 8, device=DEV)
+    rs, _ = ops.spmm_fw(rowptr, col, value.float(), ones, "sum")
+    rowsum = torch.zeros(M, device=DEV).index_add_(0, row, value.float())
+    assert torch.allclose(rs[:, 0], rowsum, rtol=1e-5, atol=1e-5)
+    # linearity: A(2x) == 2 A(x) exactly (power-of-two scaling)
+    y2, _ = ops.spmm_fw(rowptr, col, value, (x.float() * 2).bfloat16(), "sum")
+    assert torch.equal(y2.float(), (y.float() * 2).bfloat16().float())
+    # row-block decomposition
+    r0, r1 = 123_456, 345_678
+    sub = rowptr[r0:r1 + 1]
+    lo, hi = int(sub[0]), int(sub[-1])
+    ys, _ = ops.spmm_fw(sub - lo, col[lo:hi], value[lo:hi], x, "sum")
+    assert torch.equal(ys, y[r0:r1])
+    # max: arg_out points at an entry of the row whose product equals the output
+    ym, am = ops.spmm_fw(rowptr, col, value, x, "max")
+    nonempty = (rowptr[1:] - rowptr[:-1]) > 0
+    am_ne = am[nonempty]
+    assert (am_ne >= rowptr[:-1][nonempty].unsqueeze(1)).all() and (am_ne < rowptr[1:][nonempty].unsqueeze(1)).all()
+    pick = torch.randint(M, (4096,), device=DEV)
+    pick = pick[nonempty[pick]]
+    k = torch.arange(F, device=DEV)
+    a = am[pick]
+    prod = (value[a].float() * x[col[a], k.unsqueeze(0).expand_as(a)].float()).bfloat16()
+    assert torch.equal(prod, ym[pick])

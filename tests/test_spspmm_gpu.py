@@ -1,0 +1,104 @@
+"""GPU parity of SpSpMM against the oracle (Gustavson restatement of torch.sparse.mm's contract) and
+the reference's known answers (test/test_spspmm.py, test/test_matmul.py:54-79)."""
+import pytest
+import torch
+
+import pytorch_sparse_b200 as ts
+from pytorch_sparse_b200 import ops
+from util import random_csr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("dtype", [torch.float, torch.double])
+def test_functional_known_answer(dtype):
+    """test/test_spspmm.py:10-22"""
+    indexA = torch.tensor([[0, 0, 1, 2, 2], [1, 2, 0, 0, 1]], device=DEV)
+    valueA = torch.tensor([1, 2, 3, 4, 5], dtype=dtype, device=DEV)
+    indexB = torch.tensor([[0, 2], [1, 0]], device=DEV)
+    valueB = torch.tensor([2, 4], dtype=dtype, device=DEV)
+    indexC, valueC = ts.spspmm(indexA, valueA, indexB, valueB, 3, 3, 2)
+    assert indexC.tolist() == [[0, 1, 2], [0, 1, 1]]
+    assert valueC.tolist() == [8, 6, 8]
+
+
+@pytest.mark.parametrize("dtype", [torch.float, torch.double])
+def test_identity_product(dtype):
+    """test/test_matmul.py:54-77"""
+    src = torch.tensor([[1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=dtype, device=DEV)
+    src = ts.SparseTensor.from_dense(src)
+    out = ts.matmul(src, src)
+    assert out.sizes() == [3, 3]
+    assert out.has_value()
+    rowptr, col, value = out.csr()
+    assert rowptr.tolist() == [0, 1, 2, 3]
+    assert col.tolist() == [0, 1, 2]
+    assert value.tolist() == [1, 1, 1]
+    src.set_value_(None)
+    out = ts.matmul(src, src)
+    assert out.sizes() == [3, 3]
+    assert not out.has_value()
+    rowptr, col, value = out.csr()
+    assert rowptr.tolist() == [0, 1, 2, 3]
+    assert col.tolist() == [0, 1, 2]
+
+
+@pytest.mark.parametrize("dtype", [torch.float, torch.double])
+def test_orthonormal_rows(dtype):
+    """test/test_spspmm.py:25-51: x @ x.t() == I for a 10x16 matrix with orthonormal rows."""
+    x = ts.SparseTensor(
+        row=torch.tensor([0, 1, 1, 1, 2, 3, 4, 5, 5, 6, 6, 7, 7, 7, 8, 8, 9, 9], device=DEV),
+        col=torch.tensor([0, 5, 10, 15, 1, 2, 3, 7, 13, 6, 9, 5, 10, 15, 11, 14, 5, 15], device=DEV),
+        value=torch.tensor([1, 3**-0.5, 3**-0.5, 3**-0.5, 1, 1, 1, -2**-0.5, -2**-0.5, -2**-0.5, -2**-0.5, 6**-0.5,
+                            -6**0.5 / 3, 6**-0.5, -2**-0.5, -2**-0.5, 2**-0.5, -2**-0.5], dtype=dtype, device=DEV))
+    expected = torch.eye(10, device=DEV).to(dtype)
+    out = x @ x.to_dense().t()
+    assert torch.allclose(out, expected, atol=1e-2)
+    out = (x @ x.t()).to_dense()
+    assert torch.allclose(out, expected, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,Kd,N,da,db,dtype", [
+    (200, 150, 180, 6, 5, torch.float32),
+    (64, 3000, 70000, 12, 40, torch.float32),     # N > 65536
+    (50, 400, 700_000, 10, 300, torch.float64),   # N > one 2^19-column window: multi-window path
+    (30, 40, 5000, 30, 1000, torch.float32),      # rows wider than the 4096-entry shared accumulator
+])
+def test_random_vs_oracle(oracle, M, Kd, N, da, db, dtype):
+    _, rpa, ca = random_csr(M, Kd, da, seed=1, empty_rows=(0,))
+    _, rpb, cb = random_csr(Kd, N, db, seed=2, empty_rows=(1,))
+    g = torch.Generator().manual_seed(3)
+    va = torch.randn(ca.numel(), generator=g).to(dtype)
+    vb = torch.randn(cb.numel(), generator=g).to(dtype)
+    rp, r, c, v = ops.spspmm(rpa.to(DEV), ca.to(DEV), va.to(DEV), rpb.to(DEV), cb.to(DEV), vb.to(DEV), M, Kd, N, True)
+    orp, orow, oc, ov = oracle.spspmm(rpa, ca, va, rpb, cb, vb, M, Kd, N)
+    assert torch.equal(rp.cpu(), orp) and torch.equal(r.cpu(), orow) and torch.equal(c.cpu(), oc)  # bit-exact
+    tol = 1e-5 if dtype == torch.float32 else 1e-12
+    _, _, _, bound = oracle.spspmm(rpa, ca, va.abs(), rpb, cb, vb.abs(), M, Kd, N)
+    assert ((v.cpu() - ov).abs() <= tol * bound + 1e-30).all()
+    # structure-only and one-sided values
+    rp2, r2, c2, v2 = ops.spspmm(rpa.to(DEV), ca.to(DEV), None, rpb.to(DEV), cb.to(DEV), None, M, Kd, N, False)
+    assert v2 is None and torch.equal(c2.cpu(), oc)
+    rp3, r3, c3, v3 = ops.spspmm(rpa.to(DEV), ca.to(DEV), va.to(DEV), rpb.to(DEV), cb.to(DEV), None, M, Kd, N, True)
+    _, _, _, ov3 = oracle.spspmm(rpa, ca, va, rpb, cb, None, M, Kd, N)
+    assert ((v3.cpu() - ov3).abs() <= tol * bound + 1e-30).all()
+
+
+def test_structural_zeros_kept(oracle):
+    """cancelling products stay as explicit zeros (probed torch.sparse.mm behaviour)."""
+    A = ts.SparseTensor(row=torch.tensor([0, 0], device=DEV), col=torch.tensor([0, 1], device=DEV),
+                        value=torch.tensor([1., -1.], device=DEV), sparse_sizes=(1, 2))
+    B = ts.SparseTensor(row=torch.tensor([0, 1], device=DEV), col=torch.tensor([0, 0], device=DEV),
+                        value=torch.tensor([2., 2.], device=DEV), sparse_sizes=(2, 1))
+    C = A @ B
+    assert C.nnz() == 1 and C.storage.value().tolist() == [0.0]
+
+
+def test_spspmm_reduce_errors():
+    src = ts.SparseTensor.eye(3, device=DEV)
+    for red in ("mean", "min", "max"):
+        with pytest.raises(NotImplementedError):
+            ts.matmul(src, src, red)
+    with pytest.raises(RuntimeError):
+        ts.matmul(src.half(), src.half())   # "sparse_matmul" not implemented for Half
