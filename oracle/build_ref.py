@@ -65,6 +65,31 @@ def build() -> Path:
     return OUT
 
 
+ALL_LIBS = ["version", "convert", "diag", "spmm", "metis", "rw", "saint", "sample", "ego_sample", "hgt_sample",
+            "neighbor_sample", "relabel"]
+
+
+def build_full(out_dir: Path) -> Path:
+    """All 12 CPU operator libraries (what torch_sparse/__init__.py:8-21 insists on loading), so the
+    UNMODIFIED reference package can be imported for golden-vector generation. Not needed at test
+    or bench time; kept out of the repo tree."""
+    global OUT
+    out_dir.mkdir(parents=True, exist_ok=True)
+    saved, OUT = OUT, out_dir
+    try:
+        items = []
+        for n in ALL_LIBS:
+            srcs = [f"csrc/{n}.cpp"]
+            if (REF / f"csrc/cpu/{n}_cpu.cpp").exists():
+                srcs.append(f"csrc/cpu/{n}_cpu.cpp")
+            items.append((f"_{n}_cpu", srcs))
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+            list(ex.map(_one, items))
+    finally:
+        OUT = saved
+    return out_dir
+
+
 def available() -> bool:
     return all((OUT / f"{n}.so").exists() for n in LIBS)
 

@@ -1,0 +1,196 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (rusty1s/pytorch_sparse @ 91feaa5)
+in this container:
+
+  * its 12 CPU operator libraries compiled from /root/reference/csrc (oracle/build_ref.build_full,
+    into /tmp, nothing copied into the repo),
+  * its Python package imported from a scratch copy of /root/reference/torch_sparse (the package
+    loads its .so files from its own directory, torch_sparse/__init__.py:8-21, and /root/reference
+    is read-only),
+  * `torch_scatter` provided by oracle/torch_scatter_standin (third-party, absent, unpinned; only the
+    coalesce VALUE reductions and nothing else on the fixtures below go through it),
+  * SpSpMM arithmetic by torch.sparse.mm of the installed PyTorch (third-party; torch 2.11.0+cu128).
+
+    python oracle/gen_golden.py            # rewrites tests/golden/
+
+The fixtures hold inputs AND the reference's outputs, so the GPU box (where /root/reference does not
+exist) can check both the oracle and the CUDA path against the reference itself.
+"""
+from __future__ import annotations
+
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+GOLD = ROOT / "tests" / "golden"
+REF = Path("/root/reference")
+FULL = Path("/tmp/tsb200_ref_full")
+
+
+def import_reference():
+    from oracle import build_ref
+    build_ref.build_full(FULL)
+    scratch = Path(tempfile.mkdtemp(prefix="tsb200_refpkg_"))
+    shutil.copytree(REF / "torch_sparse", scratch / "torch_sparse")
+    for so in FULL.glob("*.so"):
+        shutil.copy(so, scratch / "torch_sparse" / so.name)
+    sys.path.insert(0, str(scratch))
+    sys.path.insert(0, str(ROOT / "oracle" / "torch_scatter_standin"))
+    import torch_sparse  # the reference package, unmodified
+    assert torch_sparse.__version__ == "0.6.18"
+    return torch_sparse
+
+
+def random_structure(M, N, avg_deg, seed, empty_rows=(), long_rows=()):
+    g = torch.Generator().manual_seed(seed)
+    deg = torch.poisson(torch.full((M,), float(avg_deg)), generator=g).long().clamp_(max=N)
+    for r in empty_rows:
+        deg[r] = 0
+    for r, d in long_rows:
+        deg[r] = min(d, N)
+    rows, cols = [], []
+    for m in range(M):
+        d = int(deg[m])
+        if d:
+            rows.append(torch.full((d,), m, dtype=torch.long))
+            cols.append(torch.randperm(N, generator=g)[:d].sort().values)
+    return torch.cat(rows), torch.cat(cols)
+
+
+def main():
+    ts = import_reference()
+    from torch_sparse import SparseTensor
+    from torch_sparse.matmul import matmul
+    GOLD.mkdir(parents=True, exist_ok=True)
+    meta = {"reference": "rusty1s/pytorch_sparse 0.6.18 @ 91feaa5e", "torch": torch.__version__}
+
+    # ---- (a) the reference's own SpMM test recipe (test/test_matmul.py:12-51), fwd + both grads ----
+    cases = {}
+    for dtype in (torch.float32, torch.float64, torch.float16, torch.bfloat16):
+        for reduce in ("sum", "mean", "min", "max"):
+            torch.manual_seed(12345)
+            src = torch.randn((10, 8), dtype=dtype)
+            src[2:4, :] = 0
+            src[:, 2:4] = 0
+            src = SparseTensor.from_dense(src).requires_grad_()
+            row, col, value = src.coo()
+            other = torch.randn((2, 8, 2), dtype=dtype, requires_grad=True)
+            grad_out = torch.randn((2, 10, 2), dtype=dtype)
+            out = matmul(src, other, reduce)
+            out.backward(grad_out)
+            c = dict(row=row.clone(), col=col.clone(), value=value.detach().clone(), other=other.detach().clone(),
+                     grad_out=grad_out, out=out.detach().clone(), grad_value=value.grad.clone(),
+                     grad_other=other.grad.clone())
+            if reduce in ("min", "max"):
+                rowptr, col2, val2 = src.csr()
+                fn = torch.ops.torch_sparse.spmm_min if reduce == "min" else torch.ops.torch_sparse.spmm_max
+                c["arg_out"] = fn(rowptr, col2, val2.detach(), other.detach())[1]
+            cases[f"{str(dtype).split('.')[-1]}_{reduce}"] = c
+    torch.save({"meta": meta, "cases": cases}, GOLD / "spmm_reference_recipe.pt")
+
+    # ---- (b) medium random SpMM incl. empty rows and rows longer than the kernel's segment length ----
+    cases = {}
+    M, N = 96, 300
+    row, col = random_structure(M, N, 9, seed=7, empty_rows=(0, 17, 95), long_rows=[(5, 290), (6, 256), (7, 257)])
+    rowptr = torch.ops.torch_sparse.ind2ptr(row, M)
+    g = torch.Generator().manual_seed(8)
+    for dtype, K in ((torch.float32, 32), (torch.float32, 128), (torch.bfloat16, 128), (torch.float16, 64),
+                     (torch.float64, 6), (torch.int64, 5)):
+        if dtype.is_floating_point:
+            value = torch.randn(col.numel(), generator=g).to(dtype)
+            mat = torch.randn(N, K, generator=g).to(dtype)
+        else:
+            value = torch.randint(-4, 5, (col.numel(),), generator=g)
+            mat = torch.randint(-4, 5, (N, K), generator=g)
+        c = dict(rowptr=rowptr, row=row, col=col, value=value, mat=mat)
+        for has_value in (True, False):
+            v = value if has_value else None
+            tag = "v" if has_value else "nv"
+            c[f"sum_{tag}"] = torch.ops.torch_sparse.spmm_sum(None, rowptr, col, v, None, None, mat)
+            c[f"mean_{tag}"] = torch.ops.torch_sparse.spmm_mean(None, rowptr, col, v, None, None, None, mat)
+            c[f"min_{tag}"], c[f"argmin_{tag}"] = torch.ops.torch_sparse.spmm_min(rowptr, col, v, mat)
+            c[f"max_{tag}"], c[f"argmax_{tag}"] = torch.ops.torch_sparse.spmm_max(rowptr, col, v, mat)
+        cases[f"{str(dtype).split('.')[-1]}_K{K}"] = c
+    torch.save({"meta": meta, "cases": cases}, GOLD / "spmm_medium.pt")
+
+    # ---- (c) storage views: sort-on-construct, rowptr, csr2csc, colptr (storage.py:149-162, 369-429) ----
+    g = torch.Generator().manual_seed(21)
+    M, N, E = 50, 40, 400
+    row = torch.randint(M, (E,), generator=g)
+    col = torch.randint(N, (E,), generator=g)
+    key = torch.unique(row * N + col)
+    key = key[torch.randperm(key.numel(), generator=g)]       # unique keys, shuffled => sort is well defined
+    row, col = key // N, key % N
+    value = torch.randn(row.numel(), generator=g)
+    st = ts.SparseStorage(row=row, col=col, value=value, sparse_sizes=(M, N))
+    st.fill_cache_()
+    torch.save({"meta": meta, "in": dict(row=row, col=col, value=value, M=M, N=N),
+                "out": dict(row=st.row(), col=st.col(), value=st.value(), rowptr=st.rowptr(), rowcount=st.rowcount(),
+                            colptr=st.colptr(), colcount=st.colcount(), csr2csc=st.csr2csc(), csc2csr=st.csc2csr())},
+               GOLD / "storage_views.pt")
+
+    # ---- (d) coalesce (coalesce.py:5-25). Indices come from the reference's own code; duplicate VALUE
+    #      reductions come from the torch_scatter stand-in (parity unpinned at the last ulp for float add) ----
+    g = torch.Generator().manual_seed(31)
+    M, N, E0 = 60, 50, 500
+    row = torch.randint(M, (E0,), generator=g)
+    col = torch.randint(N, (E0,), generator=g)
+    reps = torch.randint(1, 4, (E0,), generator=g)
+    row, col = row.repeat_interleave(reps), col.repeat_interleave(reps)
+    perm = torch.randperm(row.numel(), generator=g)
+    row, col = row[perm], col[perm]
+    index = torch.stack([row, col])
+    vi = torch.randint(-9, 10, (row.numel(), 2), generator=g)       # integer values: order independent
+    vf = torch.randn(row.numel(), generator=g, dtype=torch.float64)
+    outs = {}
+    for op in ("add", "mean", "min", "max"):
+        if op != "mean":
+            oi, ov = ts.coalesce(index, vi, M, N, op=op)
+            outs[f"int_{op}"] = dict(index=oi, value=ov)
+        oi, ov = ts.coalesce(index, vf, M, N, op=op)
+        outs[f"f64_{op}"] = dict(index=oi, value=ov)
+    oi, _ = ts.coalesce(index, None, M, N)
+    outs["none"] = dict(index=oi)
+    torch.save({"meta": meta, "in": dict(index=index, vi=vi, vf=vf, M=M, N=N), "out": outs}, GOLD / "coalesce.pt")
+
+    # ---- (e) transpose (transpose.py:39-62) ----
+    ti, tv = ts.transpose(index, vf, M, N)
+    torch.save({"meta": meta, "in": dict(index=index, value=vf, M=M, N=N), "out": dict(index=ti, value=tv)},
+               GOLD / "transpose.pt")
+
+    # ---- (f) SpSpMM through the reference's functional API (spspmm.py:6-33 -> torch.sparse.mm) ----
+    cases = {}
+    for name, (M, Kd, N, da, db, dtype) in {"small_f32": (40, 30, 35, 4, 5, torch.float32),
+                                            "wide_f64": (25, 60, 3000, 6, 40, torch.float64)}.items():
+        ra, ca = random_structure(M, Kd, da, seed=41, empty_rows=(0,))
+        rb, cb = random_structure(Kd, N, db, seed=42, empty_rows=(1,))
+        g = torch.Generator().manual_seed(43)
+        va = torch.randn(ra.numel(), generator=g).to(dtype)
+        vb = torch.randn(rb.numel(), generator=g).to(dtype)
+        ic, vc = ts.spspmm(torch.stack([ra, ca]), va, torch.stack([rb, cb]), vb, M, Kd, N)
+        cases[name] = dict(indexA=torch.stack([ra, ca]), valueA=va, indexB=torch.stack([rb, cb]), valueB=vb,
+                           M=M, K=Kd, N=N, indexC=ic, valueC=vc)
+    # cancellation -> explicit zero kept
+    iA = torch.tensor([[0, 0], [0, 1]]); vA = torch.tensor([1.0, -1.0])
+    iB = torch.tensor([[0, 1], [0, 0]]); vB = torch.tensor([2.0, 2.0])
+    ic, vc = ts.spspmm(iA, vA, iB, vB, 1, 2, 1)
+    cases["cancel"] = dict(indexA=iA, valueA=vA, indexB=iB, valueB=vB, M=1, K=2, N=1, indexC=ic, valueC=vc)
+    torch.save({"meta": meta, "cases": cases}, GOLD / "spspmm.pt")
+
+    # ---- (g) ind2ptr / ptr2ind (convert.cpp) ----
+    g = torch.Generator().manual_seed(51)
+    ind = torch.randint(1000, (5000,), generator=g).sort().values
+    ptr = torch.ops.torch_sparse.ind2ptr(ind, 1200)
+    back = torch.ops.torch_sparse.ptr2ind(ptr, ind.numel())
+    torch.save({"meta": meta, "ind": ind, "M": 1200, "ptr": ptr, "ind_back": back}, GOLD / "convert.pt")
+
+    sizes = {p.name: p.stat().st_size for p in sorted(GOLD.glob("*.pt"))}
+    print("wrote", sizes, "total", sum(sizes.values()))
+
+
+if __name__ == "__main__":
+    main()

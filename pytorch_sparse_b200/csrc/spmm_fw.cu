@@ -30,6 +30,7 @@ enum : int { R_SUM = TSB200_SUM, R_MEAN = TSB200_MEAN, R_MIN = TSB200_MIN, R_MAX
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kRing = 128;      // entries per warp ring (4 windows of 32)
+constexpr int kRingAlloc = kRing + 32;  // + mirror of window slot 0, so 32 consecutive entries never wrap
 constexpr int kPrefetch = 2;    // windows issued ahead of the one being consumed
 constexpr int kLongT = 256;     // rows longer than this are split into segments
 constexpr int kSeg = 256;       // nnz per segment
@@ -54,6 +55,7 @@ struct SpmmParams {
   void* out;
   int64_t* arg_out;
   int64_t B, M, N, K, E;
+  int item_shift;  // work item = (1 << item_shift) consecutive rows, <= 32
   int mean;  // SUM kernels: divide by max(count,1) at the end
   int k0;  // first column handled by this launch (column tiling for very wide K)
   // workspace
@@ -84,27 +86,31 @@ template <typename T> struct IndexRing {
   }
   __device__ __forceinline__ void issue(int w, int lane) {
     const int64_t abs0 = base + (int64_t)w * 32;
-    int64_t* dcol = s_col + ((w & 3) << 5);
+    const int ws = (w & 3) << 5;
+    const bool mirror = ws == 0;  // slots [0,32) are duplicated at [kRing, kRing+32)
     {
       const int64_t a = abs0 + lane;
       const bool ok = a < limit;
-      cp_async_zfill<8>(dcol + lane, ok ? (const void*)(col + a) : (const void*)col, ok ? 8 : 0);
+      const void* src = ok ? (const void*)(col + a) : (const void*)col;
+      cp_async_zfill<8>(s_col + ws + lane, src, ok ? 8 : 0);
+      if (mirror) cp_async_zfill<8>(s_col + kRing + lane, src, ok ? 8 : 0);
     }
     if (has_val) {
-      T* dval = s_val + ((w & 3) << 5);
       if constexpr (sizeof(T) >= 4) {
         const int64_t a = abs0 + lane;
         const bool ok = a < limit;
-        cp_async_zfill<sizeof(T)>(dval + lane,
-                                                          ok ? (const void*)(val + a) : (const void*)val,
-                                                          ok ? (int)sizeof(T) : 0);
+        const void* src = ok ? (const void*)(val + a) : (const void*)val;
+        cp_async_zfill<sizeof(T)>(s_val + ws + lane, src, ok ? (int)sizeof(T) : 0);
+        if (mirror) cp_async_zfill<sizeof(T)>(s_val + kRing + lane, src, ok ? (int)sizeof(T) : 0);
       } else {
         constexpr int EPL = 4 / sizeof(T);  // entries per lane copy
         if (lane < 32 / EPL) {
           const int64_t a = abs0 + (int64_t)lane * EPL;
-          int64_t rem = limit - a;
-          int nb = rem <= 0 ? 0 : (rem >= EPL ? 4 : (int)rem * (int)sizeof(T));
-          cp_async_zfill<4>(dval + lane * EPL, nb ? (const void*)(val + a) : (const void*)val, nb);
+          const int64_t rem = limit - a;
+          const int nb = rem <= 0 ? 0 : (rem >= EPL ? 4 : (int)rem * (int)sizeof(T));
+          const void* src = nb ? (const void*)(val + a) : (const void*)val;
+          cp_async_zfill<4>(s_val + ws + lane * EPL, src, nb);
+          if (mirror) cp_async_zfill<4>(s_val + kRing + lane * EPL, src, nb);
         }
       }
     }
@@ -127,9 +133,23 @@ template <typename T> struct IndexRing {
 };
 
 // ---- accumulator helpers -----------------------------------------------------------------------
-template <typename T, int VEC> struct Unpack;
-template <> struct Unpack<float, 4> {
-  static __device__ __forceinline__ void run(const uint4& d, float* f) {
+// Vec<T>: how one 16-byte gather of T is folded into fp32 accumulators.
+//   * bf16 / f16 use the sm_100 mixed-precision FMA (PTX fma.rn.f32.{bf16,f16} -> SASS FHFMA with
+//     .H0/.H1 operand selectors): fp32 accumulate straight from the packed 16-bit pairs, no unpack.
+//   * the nnz value travels as the raw storage bits (`vraw`), 1.0 when has_value=false.
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int VEC = 4;
+  using vraw = float;
+  static __device__ __forceinline__ vraw one() { return 1.f; }
+  static __device__ __forceinline__ float vfloat(vraw v) { return v; }
+  static __device__ __forceinline__ void fma(float* acc, vraw v, const uint4& d) {
+    acc[0] = fmaf(v, __uint_as_float(d.x), acc[0]);
+    acc[1] = fmaf(v, __uint_as_float(d.y), acc[1]);
+    acc[2] = fmaf(v, __uint_as_float(d.z), acc[2]);
+    acc[3] = fmaf(v, __uint_as_float(d.w), acc[3]);
+  }
+  static __device__ __forceinline__ void unpack(const uint4& d, float* f) {
     f[0] = __uint_as_float(d.x); f[1] = __uint_as_float(d.y);
     f[2] = __uint_as_float(d.z); f[3] = __uint_as_float(d.w);
   }
@@ -137,9 +157,23 @@ template <> struct Unpack<float, 4> {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
                       __float_as_uint(f[3]));
   }
+  static __device__ __forceinline__ float round_prod(float x) { return x; }
 };
-template <> struct Unpack<__nv_bfloat16, 8> {
-  static __device__ __forceinline__ void run(const uint4& d, float* f) {
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  using vraw = unsigned short;
+  static __device__ __forceinline__ vraw one() { return 0x3F80; }
+  static __device__ __forceinline__ float vfloat(vraw v) { return __uint_as_float((uint32_t)v << 16); }
+  static __device__ __forceinline__ void fma2(float& a0, float& a1, vraw v, uint32_t w) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, %2, lo, %0;\n\tfma.rn.f32.bf16 %1, %2, hi, %1;\n\t}"
+        : "+f"(a0), "+f"(a1) : "h"(v), "r"(w));
+  }
+  static __device__ __forceinline__ void fma(float* acc, vraw v, const uint4& d) {
+    fma2(acc[0], acc[1], v, d.x); fma2(acc[2], acc[3], v, d.y);
+    fma2(acc[4], acc[5], v, d.z); fma2(acc[6], acc[7], v, d.w);
+  }
+  static __device__ __forceinline__ void unpack(const uint4& d, float* f) {
     const uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -156,9 +190,23 @@ template <> struct Unpack<__nv_bfloat16, 8> {
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
   }
+  static __device__ __forceinline__ float round_prod(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 };
-template <> struct Unpack<__half, 8> {
-  static __device__ __forceinline__ void run(const uint4& d, float* f) {
+template <> struct Vec<__half> {
+  static constexpr int VEC = 8;
+  using vraw = unsigned short;
+  static __device__ __forceinline__ vraw one() { return 0x3C00; }
+  static __device__ __forceinline__ float vfloat(vraw v) { return __half2float(__ushort_as_half(v)); }
+  static __device__ __forceinline__ void fma2(float& a0, float& a1, vraw v, uint32_t w) {
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %3;\n\t"
+        "fma.rn.f32.f16 %0, %2, lo, %0;\n\tfma.rn.f32.f16 %1, %2, hi, %1;\n\t}"
+        : "+f"(a0), "+f"(a1) : "h"(v), "r"(w));
+  }
+  static __device__ __forceinline__ void fma(float* acc, vraw v, const uint4& d) {
+    fma2(acc[0], acc[1], v, d.x); fma2(acc[2], acc[3], v, d.y);
+    fma2(acc[4], acc[5], v, d.z); fma2(acc[6], acc[7], v, d.w);
+  }
+  static __device__ __forceinline__ void unpack(const uint4& d, float* f) {
     const uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -176,20 +224,14 @@ template <> struct Unpack<__half, 8> {
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
   }
+  // min/max compare on the product rounded to the storage type, as the reference does
+  // (csrc/cpu/spmm_cpu.cpp:81-83 forms `val * mat` in scalar_t).
+  static __device__ __forceinline__ float round_prod(float x) { return __half2float(__float2half_rn(x)); }
 };
 
-// round an fp32 product to the storage type and back (min/max compare on the rounded product,
-// as the reference does: csrc/cpu/spmm_cpu.cpp:81-83 computes `val * mat` in scalar_t).
-template <typename T> __device__ __forceinline__ float round_to(float x) { return x; }
-template <> __device__ __forceinline__ float round_to<__nv_bfloat16>(float x) {
-  return __bfloat162float(__float2bfloat16_rn(x));
-}
-template <> __device__ __forceinline__ float round_to<__half>(float x) {
-  return __half2float(__float2half_rn(x));
-}
-
 template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
-  static constexpr int VEC = 16 / sizeof(T);
+  using V = Vec<T>;
+  static constexpr int VEC = V::VEC;
   static constexpr int G = 32 / LPR;
   static constexpr int NA = VEC * CH;
   static constexpr bool ARG = (RED == R_MIN || RED == R_MAX);
@@ -210,59 +252,90 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
     }
   }
 
-  // accumulate ring-relative nnz [s, e) of one row; `matb` already points at this lane's
-  // first column of batch b.
+  // one step of the min/max update (compare on the product rounded to the storage type)
+  __device__ __forceinline__ void minmax_step(float* a, int* ar, typename V::vraw v, const uint4& d, int jabs) {
+    float f[VEC];
+    V::unpack(d, f);
+    const float vf = V::vfloat(v);
+#pragma unroll
+    for (int i = 0; i < VEC; i++) {
+      const float p = V::round_prod(vf * f[i]);  // v == 1 when has_value=false => p == f
+      const bool better = (RED == R_MIN) ? (p < a[i]) : (p > a[i]);
+      if (better) {
+        a[i] = p;
+        ar[i] = jabs;
+      }
+    }
+  }
+
+  // accumulate ring-relative nnz [s, e) of one row. `matb` points at this lane's first column of
+  // batch b. The row is walked in chunks of up to U steps (a step = G nnz, one per lane group);
+  // every step of a chunk issues its 128-bit gather before the first FMA of the chunk. Full chunks
+  // take an unpredicated path; the (warp-uniform) step count of the last chunk is honoured exactly
+  // with early exits — no padded work. Thanks to the ring mirror the <= 32 entries of a chunk are
+  // contiguous in shared memory: one base pointer, immediate offsets.
   __device__ __forceinline__ void accumulate(IndexRing<T>& ring, int s, int e,
-                                             const char* __restrict__ matb, int64_t row_bytes,
-                                             bool col_ok[CH], int lane, int g, uint64_t pol) {
+                                             const char* __restrict__ matb, uint32_t row_bytes,
+                                             const bool (&col_ok)[CH], int lane, int g, uint64_t pol) {
+    using VR = typename V::vraw;
     for (int j0 = s; j0 < e; j0 += U * G) {
       const int jend = min(e, j0 + U * G);
       ring.ensure(j0, jend, lane);
+      const int slot0 = (j0 + g) & (kRing - 1);
+      const uint32_t* pc = reinterpret_cast<const uint32_t*>(ring.s_col + slot0);  // low words (N < 2^32)
+      const VR* pv = reinterpret_cast<const VR*>(ring.s_val) + slot0;
+      const int jabs0 = (int)ring.base + j0 + g;  // absolute nnz index of step 0 (E < 2^31)
       uint4 d[U][CH];
-      float v[U];
-      bool act[U];
+      VR v[U];
+      if (jend - j0 == U * G) {  // full chunk: every lane group has work in every step
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int j = j0 + u * G + g;
-        act[u] = j < jend;
-        const int slot = j & (kRing - 1);
-        const int64_t c = ring.s_col[slot];
-        // inactive lanes must contribute exactly +0 (stale ring bytes may be NaN/Inf)
-        v[u] = act[u] ? (ring.has_val ? Traits<T>::to_acc(ring.s_val[slot]) : 1.f) : 0.f;
-        const char* src = matb + c * row_bytes;
+        for (int u = 0; u < U; u++) {
+          const uint32_t c = pc[2 * u * G];
+          v[u] = pv[u * G];
+          const char* src = matb + (uint64_t)c * row_bytes;
 #pragma unroll
-        for (int ch = 0; ch < CH; ch++) {
-          if (act[u] && col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
-          else d[u][ch] = make_uint4(0, 0, 0, 0);
+          for (int ch = 0; ch < CH; ch++)
+            if (col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
         }
-      }
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const int jabs = (int)((ring.base + j0 + u * G + g));  // absolute nnz index (E < 2^31)
+        for (int u = 0; u < U; u++) {
 #pragma unroll
-        for (int ch = 0; ch < CH; ch++) {
-          float f[VEC];
-          Unpack<T, VEC>::run(d[u][ch], f);
+          for (int ch = 0; ch < CH; ch++) {
+            if (!col_ok[ch]) continue;
+            if (RED == R_SUM) V::fma(&acc[ch * VEC], v[u], d[u][ch]);
+            else minmax_step(&acc[ch * VEC], &arg[ch * VEC], v[u], d[u][ch], jabs0 + u * G);
+          }
+        }
+      } else {
+        const int nst = (jend - j0 + G - 1) / G;  // steps in this chunk, 1..U (warp-uniform)
+        const int jrel = jend - j0 - g;            // lane group g is active in step u iff u*G < jrel
+        bool act[U];
 #pragma unroll
-          for (int i = 0; i < VEC; i++) {
-            if (RED == R_SUM) {
-              // inactive lanes carry d = 0 => contribute +0
-              acc[ch * VEC + i] = fmaf(v[u], f[i], acc[ch * VEC + i]);  // v == 1 when has_value=false
-            } else {
-              const float p = round_to<T>(v[u] * f[i]);  // v == 1 => p == f exactly
-              const bool better = (RED == R_MIN) ? (p < acc[ch * VEC + i]) : (p > acc[ch * VEC + i]);
-              if (act[u] && better) {
-                acc[ch * VEC + i] = p;
-                arg[ch * VEC + i] = jabs;
-              }
-            }
+        for (int u = 0; u < U; u++) {
+          if (u >= nst) break;
+          act[u] = u * G < jrel;
+          const uint32_t c = pc[2 * u * G];
+          v[u] = pv[u * G];
+          const char* src = matb + (uint64_t)c * row_bytes;
+#pragma unroll
+          for (int ch = 0; ch < CH; ch++)
+            if (act[u] && col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (u >= nst) break;
+#pragma unroll
+          for (int ch = 0; ch < CH; ch++) {
+            if (!(act[u] && col_ok[ch])) continue;
+            if (RED == R_SUM) V::fma(&acc[ch * VEC], v[u], d[u][ch]);
+            else minmax_step(&acc[ch * VEC], &arg[ch * VEC], v[u], d[u][ch], jabs0 + u * G);
           }
         }
       }
     }
   }
 
-  // combine the G lane groups; afterwards group 0 holds the row result.
+  // combine the G lane groups; afterwards every group holds the row result.
   __device__ __forceinline__ void reduce_groups() {
 #pragma unroll
     for (int off = LPR; off < 32; off <<= 1) {
@@ -285,7 +358,7 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
 
   // final write of one row (group 0 lanes). count = row degree.
   __device__ __forceinline__ void store_row(T* __restrict__ out_row, int64_t* __restrict__ arg_row,
-                                            int64_t count, int64_t E, bool col_ok[CH], int li,
+                                            int64_t count, int64_t E, const bool (&col_ok)[CH], int li,
                                             bool mean) {
 #pragma unroll
     for (int ch = 0; ch < CH; ch++) {
@@ -299,7 +372,7 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
         f[i] = a;
       }
       const int koff = (ch * LPR + li) * VEC;
-      stg128_stream(out_row + koff, Unpack<T, VEC>::pack(f));
+      stg128_stream(out_row + koff, V::pack(f));
       if (ARG) {
 #pragma unroll
         for (int i = 0; i < VEC; i += 2) {
@@ -313,13 +386,13 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
   }
 };
 
-template <typename T, int RED, int LPR, int CH, int U>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <typename T, int RED, int LPR, int CH, int U, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_vec_kernel(const SpmmParams p) {
   using Eng = RowEngine<T, RED, LPR, CH, U>;
   constexpr int VEC = Eng::VEC;
-  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRing];
-  __shared__ __align__(16) T s_val[kWarpsPerCta][kRing];
+  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRingAlloc];
+  __shared__ __align__(16) T s_val[kWarpsPerCta][kRingAlloc];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / LPR, li = lane % LPR;
@@ -328,6 +401,11 @@ spmm_vec_kernel(const SpmmParams p) {
   ring.s_col = s_col[warp];
   ring.s_val = s_val[warp];
   ring.has_val = p.value != nullptr;
+  if (!ring.has_val) {  // has_value=false: the ring's value half is a constant 1
+    using VR = typename Vec<T>::vraw;
+    for (int i = lane; i < kRingAlloc; i += 32) reinterpret_cast<VR*>(s_val[warp])[i] = Vec<T>::one();
+    __syncwarp();
+  }
   ring.col = p.col;
   ring.val = (const T*)p.value;
   ring.limit = p.E;
@@ -336,10 +414,11 @@ spmm_vec_kernel(const SpmmParams p) {
   bool col_ok[CH];
 #pragma unroll
   for (int ch = 0; ch < CH; ch++) col_ok[ch] = p.k0 + (ch * LPR + li) * VEC < p.K;
-  const int64_t row_bytes = p.K * (int64_t)sizeof(T);
+  const uint32_t row_bytes = (uint32_t)(p.K * (int64_t)sizeof(T));
   const int64_t lane_off = ((int64_t)p.k0 + (int64_t)li * VEC) * (int64_t)sizeof(T);
 
-  const int64_t nblk = (p.M + 31) >> 5;
+  const int item_rows = 1 << p.item_shift;
+  const int64_t nblk = (p.M + item_rows - 1) >> p.item_shift;
   const int64_t n_items = nblk * p.B;
 
   unsigned int item = 0;
@@ -351,8 +430,8 @@ spmm_vec_kernel(const SpmmParams p) {
     if (lane == 0) next_item = atomicAdd(&p.counters[0], 1u);  // latency hidden behind this item
 
     const int64_t b = item / nblk, blk = item - b * nblk;
-    const int64_t r0 = blk << 5;
-    const int nrows = (int)min((int64_t)32, p.M - r0);
+    const int64_t r0 = blk << p.item_shift;
+    const int nrows = (int)min((int64_t)item_rows, p.M - r0);
     const int64_t rp0 = __ldg(p.rowptr + r0 + min(lane, nrows));
     const int64_t rp1 = __ldg(p.rowptr + r0 + min(lane + 1, nrows));
     const int64_t a0 = __shfl_sync(0xffffffffu, rp0, 0);
@@ -400,7 +479,8 @@ spmm_vec_kernel(const SpmmParams p) {
     __syncwarp();
 
     ring.reset(base);
-    const char* matb = (const char*)p.mat + b * p.N * row_bytes + lane_off;
+    const char* matb = (const char*)p.mat + b * p.N * (int64_t)row_bytes + lane_off;
+    asm volatile("" : "+l"(matb));  // keep the gather base in a register
     T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0;
     int64_t* argb = p.arg_out ? p.arg_out + (b * p.M + r0) * p.K + p.k0 : nullptr;
 
@@ -419,13 +499,13 @@ spmm_vec_kernel(const SpmmParams p) {
 }
 
 // one warp per queued segment
-template <typename T, int RED, int LPR, int CH, int U>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <typename T, int RED, int LPR, int CH, int U, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_seg_kernel(const SpmmParams p) {
   using Eng = RowEngine<T, RED, LPR, CH, U>;
   constexpr int VEC = Eng::VEC;
-  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRing];
-  __shared__ __align__(16) T s_val[kWarpsPerCta][kRing];
+  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRingAlloc];
+  __shared__ __align__(16) T s_val[kWarpsPerCta][kRingAlloc];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane / LPR, li = lane % LPR;
 
@@ -433,6 +513,11 @@ spmm_seg_kernel(const SpmmParams p) {
   ring.s_col = s_col[warp];
   ring.s_val = s_val[warp];
   ring.has_val = p.value != nullptr;
+  if (!ring.has_val) {  // has_value=false: the ring's value half is a constant 1
+    using VR = typename Vec<T>::vraw;
+    for (int i = lane; i < kRingAlloc; i += 32) reinterpret_cast<VR*>(s_val[warp])[i] = Vec<T>::one();
+    __syncwarp();
+  }
   ring.col = p.col;
   ring.val = (const T*)p.value;
   ring.limit = p.E;
@@ -441,7 +526,7 @@ spmm_seg_kernel(const SpmmParams p) {
   bool col_ok[CH];
 #pragma unroll
   for (int ch = 0; ch < CH; ch++) col_ok[ch] = p.k0 + (ch * LPR + li) * VEC < p.K;
-  const int64_t row_bytes = p.K * (int64_t)sizeof(T);
+  const uint32_t row_bytes = (uint32_t)(p.K * (int64_t)sizeof(T));
   const int64_t lane_off = ((int64_t)p.k0 + (int64_t)li * VEC) * (int64_t)sizeof(T);
 
   const int64_t nseg = min((int64_t)p.counters[1], p.seg_cap);
@@ -451,7 +536,8 @@ spmm_seg_kernel(const SpmmParams p) {
     const int64_t b = S.row_b / p.M, row = S.row_b - b * p.M;
     const int64_t base = S.start & ~(int64_t)31;
     ring.reset(base);
-    const char* matb = (const char*)p.mat + b * p.N * row_bytes + lane_off;
+    const char* matb = (const char*)p.mat + b * p.N * (int64_t)row_bytes + lane_off;
+    asm volatile("" : "+l"(matb));
     Eng eng;
     eng.init();
     eng.accumulate(ring, (int)(S.start - base), (int)(S.end - base), matb, row_bytes, col_ok, lane, g, pol);
@@ -591,10 +677,10 @@ static bool vec_eligible(int dtype, int64_t K, int64_t E, int64_t N, const void*
   const size_t es = dtype_size(dtype);
   if ((K * es) % 16 != 0) return false;
   if (E >= ((int64_t)1 << 31) - 64) return false;
+  if (N >= ((int64_t)1 << 32) || K * (int64_t)es >= ((int64_t)1 << 31)) return false;
   if (((uintptr_t)mat & 15) || ((uintptr_t)out & 15) || ((uintptr_t)col & 7)) return false;
   if (value && ((uintptr_t)value & 3)) return false;
   if (arg_out && ((uintptr_t)arg_out & 15)) return false;
-  (void)N;
   return true;
 }
 
@@ -607,16 +693,20 @@ static int grid_for(const void* kernel, int threads) {
   return per_sm * sms;
 }
 
-template <typename T, int RED, int LPR, int CH, int U>
+template <typename T, int RED, int LPR, int CH, int U, int MINB = 1>
 static int launch_vec(SpmmParams p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int kcols = LPR * CH * VEC;
-  auto* kmain = spmm_vec_kernel<T, RED, LPR, CH, U>;
-  auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, U>;
+  auto* kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB>;
+  auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, U, MINB>;
   static int grid_main = 0, grid_seg = 0;  // per-instantiation cache
   if (!grid_main) grid_main = grid_for((const void*)kmain, kWarpsPerCta * 32);
   if (!grid_seg) grid_seg = grid_for((const void*)kseg, kWarpsPerCta * 32);
-  const int64_t n_items = ((p.M + 31) >> 5) * p.B;
+  // small matrices: shrink the work item so that every resident warp gets rows
+  int64_t want = p.M * p.B / ((int64_t)grid_main * kWarpsPerCta * 2);
+  p.item_shift = 0;
+  while (p.item_shift < 5 && ((int64_t)2 << p.item_shift) <= want) p.item_shift++;
+  const int64_t n_items = ((p.M + (1 << p.item_shift) - 1) >> p.item_shift) * p.B;
   for (int k0 = 0; k0 < p.K; k0 += kcols) {
     p.k0 = k0;
     TSB_CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));
@@ -631,16 +721,19 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
   return 0;
 }
 
+// (LPR, CH) follow from the width of a dense row; (U, MINB) = gathers in flight per lane and CTAs
+// per SM, tuned on B200 (profiles/r01_variant_sweep.txt): the kernel is HBM-latency bound, so
+// resident warps x gathers-in-flight wins; 40 warps/SM x 4 x 16 B per lane saturates HBM.
 template <typename T, int RED> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   const int64_t vecs = p.K / VEC;  // 16-byte vectors per dense row
-  if (vecs <= 1) return launch_vec<T, RED, 1, 1, 1>(p, st);
-  if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4>(p, st);
-  if (vecs <= 8) return launch_vec<T, RED, 8, 1, 4>(p, st);
-  if (vecs <= 16) return launch_vec<T, RED, 16, 1, 8>(p, st);
-  if (vecs <= 32) return launch_vec<T, RED, 32, 1, 8>(p, st);
-  if (vecs <= 64) return launch_vec<T, RED, 32, 2, 4>(p, st);
-  return launch_vec<T, RED, 32, 4, 2>(p, st);  // column-tiled beyond 128 vectors
+  if (vecs <= 1) return launch_vec<T, RED, 1, 1, 1, 6>(p, st);
+  if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4, 5>(p, st);
+  if (vecs <= 8) return launch_vec<T, RED, 8, 1, 4, 5>(p, st);
+  if (vecs <= 16) return launch_vec<T, RED, 16, 1, 4, 5>(p, st);
+  if (vecs <= 32) return launch_vec<T, RED, 32, 1, 4, 5>(p, st);
+  if (vecs <= 64) return launch_vec<T, RED, 32, 2, 4, 3>(p, st);
+  return launch_vec<T, RED, 32, 4, 2, 3>(p, st);  // column-tiled beyond 128 vectors
 }
 
 template <typename T> static int dispatch_red_vec(SpmmParams p, int reduce, cudaStream_t st) {
@@ -700,7 +793,7 @@ extern "C" int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
     char* ws = (char*)workspace;
     SpmmParams p;
     p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = arg_out;
-    p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0;
+    p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
     p.counters = (unsigned int*)(ws + L.counters);
     p.segs = (Segment*)(ws + L.segs);
     p.longs = (LongRow*)(ws + L.longs);
