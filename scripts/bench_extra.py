@@ -1,0 +1,115 @@
+"""Secondary measurements of the hot path (not the driver bench): C3 SpMM_max fwd+bwd, C4 SpSpMM,
+coalesce, csr2csc, SpMM backward, PCIe bandwidth. Prints one JSON object per line."""
+import json, sys, time
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+import torch
+import pytorch_sparse_b200 as ts
+from pytorch_sparse_b200 import ops
+from util import fast_random_csr
+
+dev = "cuda:0"
+which = set(sys.argv[1:]) or {"pcie", "c2bw", "c3", "c4", "coalesce", "csc"}
+
+
+def timeit(fn, steps=10, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def out(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+if "pcie" in which:
+    h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms_up = timeit(lambda: d.copy_(h, non_blocking=True), 5, 1)
+    ms_dn = timeit(lambda: h.copy_(d, non_blocking=True), 5, 1)
+    out(what="pcie_pinned_256MB", h2d_gbs=256 / 1024 / ms_up * 1e3, d2h_gbs=256 / 1024 / ms_dn * 1e3)
+
+if "c2bw" in which:  # SpMM_sum fwd+bwd at C2 (value grad + dense grad)
+    M = 1_000_000; F = 128
+    row, rowptr, col = fast_random_csr(M, M, 16, 1, dev)
+    E = col.numel()
+    a = ts.SparseTensor(row=row, rowptr=rowptr, col=col, value=(torch.rand(E, device=dev) + 0.5).bfloat16(),
+                        sparse_sizes=(M, M), is_sorted=True, trust_data=True).requires_grad_()
+    x = torch.randn(M, F, device=dev).bfloat16().requires_grad_()
+    go = torch.randn(M, F, device=dev).bfloat16()
+    t_csc = timeit(lambda: (a.storage.clear_cache_(), a.storage.csr2csc()), 5, 1)
+    a.storage.fill_cache_()
+    t_f = timeit(lambda: a @ x.detach(), 20, 3)
+    def fb():
+        x.grad = None; a.storage.value().grad = None
+        (a @ x).backward(go)
+    t_fb = timeit(fb, 10, 2)
+    t_vbw = timeit(lambda: ops.spmm_value_bw(row, rowptr, col, x.detach(), go, "sum"), 10, 2)
+    out(what="c2_sum_bf16_F128", fwd_ms=t_f, fwd_bwd_ms=t_fb, value_bw_ms=t_vbw, csr2csc_colptr_ms=t_csc, E=E)
+
+if "c3" in which:  # SpMM_max fwd + bwd, power-law, F=256 fp32 (BASELINE configs[2])
+    import bench
+    w = bench.WORKLOADS["c3"]
+    rowptr, col, value, N = bench.gen_matrix(w, 0, 1)
+    M, F = w["M"], w["F"]
+    rowptr, col, value = rowptr.to(dev), col.to(dev), value.to(dev)
+    E = col.numel()
+    deg = rowptr[1:] - rowptr[:-1]
+    a = ts.SparseTensor(rowptr=rowptr, col=col, value=value, sparse_sizes=(M, N), is_sorted=True, trust_data=True).requires_grad_()
+    x = torch.randn(N, F, device=dev).requires_grad_()
+    go = torch.randn(M, F, device=dev)
+    t_f = timeit(lambda: a.matmul(x.detach(), "max"), 10, 2)
+    def fb():
+        x.grad = None; a.storage.value().grad = None
+        a.matmul(x, "max").backward(go)
+    t_fb = timeit(fb, 5, 2)
+    out(what="c3_max_f32_F256_powerlaw", fwd_ms=t_f, fwd_bwd_ms=t_fb, E=E, max_deg=int(deg.max()), empty_rows=int((deg == 0).sum()),
+        fwd_alg_gbs=bench.algorithmic_bytes(M, N, E, F, 4, True) / t_f / 1e6)
+
+if "c4" in which:  # SpSpMM 256k x 256k, 32 nnz/row, fp32 (BASELINE configs[3])
+    M = 262_144
+    ra, rpa, ca = fast_random_csr(M, M, 32, 3, dev)
+    rb, rpb, cb = fast_random_csr(M, M, 32, 4, dev)
+    va = torch.randn(ca.numel(), device=dev); vb = torch.randn(cb.numel(), device=dev)
+    res = {}
+    def run():
+        res["c"] = ops.spspmm(rpa, ca, va, rpb, cb, vb, M, M, M, True)
+    torch.cuda.synchronize(); t0 = time.perf_counter(); run(); torch.cuda.synchronize(); t_first = (time.perf_counter() - t0) * 1e3
+    t = timeit(run, 3, 0)
+    nnz = res["c"][2].numel()
+    del res
+    out(what="c4_spspmm_f32", ms=t, first_ms=t_first, nnz_a=ca.numel(), nnz_b=cb.numel(), nnz_c=nnz, out_gbs=nnz * 20 / t / 1e6,
+        Gnnz_per_s=nnz / t / 1e6)
+
+if "coalesce" in which:
+    M = N = 262_144
+    g = torch.Generator(device=dev).manual_seed(5)
+    E0 = 4_194_304
+    row = torch.randint(M, (E0,), generator=g, device=dev); col = torch.randint(N, (E0,), generator=g, device=dev)
+    perm = torch.randperm(2 * E0, generator=g, device=dev)
+    row2, col2 = torch.cat([row, row])[perm], torch.cat([col, col])[perm]
+    val = torch.randn(2 * E0, device=dev)
+    t = timeit(lambda: ops.coalesce(row2, col2, val, M, N, "add"), 5, 1)
+    t_sorted = timeit(lambda: ops.coalesce(*ops.coalesce(row2, col2, val, M, N, "add")[:2], None, M, N, "add"), 3, 1)
+    def ref():
+        key = row2 * N + col2
+        k, inv = torch.unique(key, return_inverse=True)
+        return torch.zeros(k.numel(), device=dev).index_add_(0, inv, val)
+    t_torch = timeit(ref, 3, 1)
+    out(what="coalesce_8.4M_shuffled_dup", ms=t, Mkeys_per_s=2 * E0 / t / 1e3, torch_unique_index_add_ms=t_torch)
+
+if "csc" in which:
+    M = 1_000_000
+    row, rowptr, col = fast_random_csr(M, M, 16, 1, dev)
+    t = timeit(lambda: ops.csr2csc(row, col, M, M, True, True), 5, 1)
+    t_i2p = timeit(lambda: ops.ind2ptr(row, M), 10, 2)
+    t_p2i = timeit(lambda: ops.ptr2ind(rowptr, col.numel()), 10, 2)
+    t_torch = timeit(lambda: torch.sort(col * M + row)[1], 3, 1)
+    out(what="format_16M", csr2csc_ms=t, ind2ptr_ms=t_i2p, ptr2ind_ms=t_p2i, torch_sort_linearised_ms=t_torch)

@@ -1,0 +1,189 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/tsb200.h, argument
+validation that needs no GPU, the Python host logic (autograd wiring, optional-argument rules,
+cache management, row sharding over gloo) with the oracle standing in for the CUDA kernels."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+import pytorch_sparse_b200 as ts
+from pytorch_sparse_b200 import _lib, ops
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "tsb200.h").read_text()
+    declared = set(re.findall(r"TSB200_API\s+[\w\s\*]+?\b(tsb200_\w+)\s*\(", header))
+    assert len(declared) >= 19
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(_lib.lib, name), name
+    assert _lib.lib.tsb200_version() == 100
+    assert _lib.strerror(0) == "success" and "workspace" in _lib.strerror(-3)
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.lib
+    assert lib.tsb200_spmm_fw(None, None, None, None, None, None, 1, -1, 1, 1, 1, 0, 0, None, 0, None) == -1
+    assert lib.tsb200_spmm_fw(None, None, None, None, None, None, 1, 4, 4, 4, 4, 0, 9, None, 0, None) == -1
+    assert lib.tsb200_spmm_fw(None, None, None, None, None, None, 1, 4, 4, 4, 4, 99, 0, None, 0, None) == -1
+    assert lib.tsb200_spmm_fw(None, None, None, None, None, None, 1, 0, 4, 4, 0, 0, 0, None, 0, None) == 0  # empty
+    assert lib.tsb200_spmm_fw_workspace_bytes(1, 1000, 128, 16000, 3, 0) > 0
+    assert lib.tsb200_spmm_fw_workspace_bytes(1, 1000, 128, 16000, 5, 0) == 0      # int64: generic kernel
+    assert lib.tsb200_coalesce_workspace_bytes(1000, 10, 10) > 16 * 1000
+    assert lib.tsb200_spmm_value_bw(None, None, None, None, None, None, 1, 4, 4, 4, 4, 0, 2, None) == -1  # reduce=min
+
+
+def test_ops_reject_cpu_tensors():
+    rowptr, col = torch.tensor([0, 1]), torch.tensor([0])
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        ops.spmm_fw(rowptr, col, None, torch.ones(1, 4), "sum")
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        ops.ind2ptr(col, 1)
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        ops.coalesce(col, col, None, 1, 1)
+    a = ts.SparseTensor(row=col, col=col, value=torch.ones(1), sparse_sizes=(1, 1))
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        a @ torch.ones(1, 4)
+
+
+def test_storage_host_bookkeeping_matches_reference_known_answers():
+    """test/test_storage.py:27-92 on CPU-resident tensors (construction convenience path)."""
+    st = ts.SparseStorage(row=torch.tensor([0, 0, 1, 1]), col=torch.tensor([1, 0, 1, 0]),
+                          value=torch.tensor([2., 1., 4., 3.]))
+    assert st.row().tolist() == [0, 0, 1, 1] and st.col().tolist() == [0, 1, 0, 1]
+    assert st.value().tolist() == [1, 2, 3, 4] and st.sparse_sizes() == (2, 2)
+    assert st.num_cached_keys() == 0
+    st.fill_cache_()
+    assert st._rowptr.tolist() == [0, 2, 4] and st._colptr.tolist() == [0, 2, 4]
+    assert st._csr2csc.tolist() == [0, 2, 1, 3] and st._csc2csr.tolist() == [0, 2, 1, 3]
+    assert st.cached_keys() == ["rowcount", "colptr", "colcount", "csr2csc", "csc2csr"]
+    t = ts.SparseTensor.from_storage(st).t()
+    assert t.storage.row().tolist() == [0, 0, 1, 1] and t.storage.value().tolist() == [1, 3, 2, 4]
+    assert st.clear_cache_().num_cached_keys() == 0
+
+
+@pytest.fixture
+def oracle_kernels(monkeypatch, oracle):
+    """Route the tensor-level kernels of ops.py through the oracle so the HOST logic (autograd
+    Functions, argument rules, matmul dispatch) can be exercised on a machine without a GPU."""
+    monkeypatch.setattr(ops, "spmm_fw", lambda rowptr, col, value, mat, reduce: oracle.spmm(rowptr, col, value, mat, reduce))
+    monkeypatch.setattr(ops, "spmm_value_bw", oracle.spmm_value_bw)
+    monkeypatch.setattr(ops, "spmm_minmax_bw",
+                        lambda col, value, mat, go, arg, nv, nm: oracle.spmm_minmax_bw(col, value, mat, go, arg, nv, nm))
+    return oracle
+
+
+@pytest.mark.parametrize("reduce", ["sum", "add", "mean", "min", "max"])
+def test_autograd_wiring_like_reference_test(oracle_kernels, reduce):
+    """test/test_matmul.py:12-51 end to end through SparseTensor / matmul / autograd Functions."""
+    torch.manual_seed(0)
+    dense = torch.randn(10, 8, dtype=torch.float64)
+    dense[2:4, :] = 0
+    dense[:, 2:4] = 0
+    src = ts.SparseTensor.from_dense(dense).requires_grad_()
+    row, col, value = src.coo()
+    other = torch.randn(2, 8, 2, dtype=torch.float64, requires_grad=True)
+    v2, o2 = value.detach().clone().requires_grad_(), other.detach().clone().requires_grad_()
+    src_col = o2.index_select(-2, col) * v2.unsqueeze(-1)
+    if reduce in ("sum", "add", "mean"):
+        exp = torch.zeros(2, 10, 2, dtype=torch.float64).index_add(-2, row, src_col)
+        if reduce == "mean":
+            exp = exp / torch.bincount(row, minlength=10).clamp(min=1).view(1, 10, 1)
+    else:
+        fill = float("inf") if reduce == "min" else float("-inf")
+        idx = row.view(1, -1, 1).expand_as(src_col)
+        exp = torch.full((2, 10, 2), fill, dtype=torch.float64).scatter_reduce(
+            -2, idx, src_col, reduce="amin" if reduce == "min" else "amax", include_self=True)
+        exp = torch.where(torch.isinf(exp), torch.zeros_like(exp), exp)
+    go = torch.randn_like(exp)
+    exp.backward(go)
+    out = ts.matmul(src, other, reduce)
+    out.backward(go)
+    assert torch.allclose(exp, out, atol=1e-10)
+    assert torch.allclose(v2.grad, value.grad, atol=1e-10)
+    assert torch.allclose(o2.grad, other.grad, atol=1e-10)
+
+
+def test_optional_argument_rules(oracle_kernels):
+    """csrc/spmm.cpp:64-72: row / colptr / csr2csc are required exactly when a gradient needs them."""
+    src = ts.SparseTensor.from_dense(torch.eye(3, dtype=torch.float64))
+    rowptr, col, value = src.csr()
+    x = torch.randn(3, 2, dtype=torch.float64)
+    assert torch.allclose(ops.spmm_sum(None, rowptr, col, value, None, None, x), x)
+    with pytest.raises(RuntimeError, match="Argument `row` is missing"):
+        ops.spmm_sum(None, rowptr, col, value, None, None, x.clone().requires_grad_())
+    with pytest.raises(RuntimeError, match="Argument `row` is missing"):
+        ops.spmm_sum(None, rowptr, col, value.clone().requires_grad_(), None, None, x)
+    with pytest.raises(RuntimeError, match="Argument `colptr` is missing"):
+        ops.spmm_sum(src.storage.row(), rowptr, col, value, None, None, x.clone().requires_grad_())
+    with pytest.raises(RuntimeError, match="Argument `rowcount` is missing"):
+        ops.spmm_mean(src.storage.row(), rowptr, col, value, None, src.storage.colptr(), src.storage.csr2csc(),
+                      x.clone().requires_grad_())
+    with pytest.raises(ValueError):
+        ts.matmul(src, x, "prod")
+    with pytest.raises(NotImplementedError):
+        ts.matmul(src, src, "max")
+    o, a = ops.spmm_max(rowptr, col, None, x)
+    assert a.dtype == torch.long and not a.requires_grad
+
+
+def test_matmul_materialises_only_needed_caches(oracle_kernels):
+    """torch_sparse/matmul.py:19-25: csr2csc/colptr are built only when `other` needs a gradient."""
+    src = ts.SparseTensor.from_dense(torch.rand(6, 5, dtype=torch.float64).round())
+    x = torch.randn(5, 3, dtype=torch.float64)
+    src @ x
+    assert src.storage.num_cached_keys() == 0
+    (src @ x.requires_grad_()).sum().backward()
+    assert set(src.storage.cached_keys()) >= {"colptr", "csr2csc"}
+
+
+_GLOO = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, "%(root)s"); sys.path.insert(0, "%(root)s/tests")
+import oracle
+import pytorch_sparse_b200 as ts
+from pytorch_sparse_b200 import ops
+from pytorch_sparse_b200.parallel import RowShardedSpMM
+ops.spmm_fw = lambda rowptr, col, value, mat, reduce: oracle.spmm(rowptr, col, value, mat, reduce)
+ops.spmm_value_bw = oracle.spmm_value_bw
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+g = torch.Generator().manual_seed(0)
+M = N = 64; K = 8
+dense = (torch.rand(M, N, generator=g) < 0.1).double() * torch.randn(M, N, generator=g, dtype=torch.float64)
+x = torch.randn(N, K, generator=g, dtype=torch.float64)
+full = ts.SparseTensor.from_dense(dense)
+a_local = RowShardedSpMM.partition(full, rank, world)
+per = M // world
+x_local = x[rank * per:(rank + 1) * per].clone().requires_grad_()
+op = RowShardedSpMM(a_local.requires_grad_(), "sum")
+y_local = op(x_local)
+ref = dense @ x
+assert torch.allclose(y_local, ref[rank * per:(rank + 1) * per], atol=1e-12), "forward shard mismatch"
+go = torch.randn(M, K, generator=g, dtype=torch.float64)
+y_local.backward(go[rank * per:(rank + 1) * per])
+gx = dense.t() @ go                      # needs the reduce-scatter of the per-rank partials
+assert torch.allclose(x_local.grad, gx[rank * per:(rank + 1) * per], atol=1e-12), "grad_X shard mismatch"
+assert a_local.storage.value().grad is not None
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_row_sharded_spmm_gloo_world2(oracle, tmp_path):
+    """N>1 path on CPU: 2 ranks over gloo, row-block partition, all-gather of X, local SpMM (oracle
+    kernels), reduce-scatter of grad_X — forward and backward match the dense product."""
+    script = tmp_path / "gloo_worker.py"
+    script.write_text(_GLOO % {"root": str(ROOT)})
+    env = dict(os.environ, TSB200_REGISTER_TORCH_SPARSE="0")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    assert out.stdout.count("ok") == 2
