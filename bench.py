@@ -249,6 +249,9 @@ def run_ours(args, w):
                               sparse_sizes=(M, N), is_sorted=True, trust_data=True)
     sharded = RowShardedSpMM(a_local, reduce=reduce)
     # dense operand made resident on every GPU ONCE over NVLink (north_star: "broadcast once")
+    if world > 1:  # NCCL communicator setup is not part of the gather time
+        dist.all_reduce(torch.zeros(1, device=dev))
+        sharded.gather_dense(x_local_h.to(dev))
     torch.cuda.synchronize()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -323,7 +326,7 @@ def run_ours(args, w):
         achieved = abytes / (ms_step * 1e-3) / 1e9
         traffic = None
         tf = ROOT / "profiles" / "ncu_traffic.json"
-        if tf.exists():
+        if tf.exists() and world == 1:  # ncu capture of the N=1 launch (profiles/r01_ncu_spmm_c2.md)
             traffic = json.loads(tf.read_text()).get(args.workload)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:

@@ -5,6 +5,7 @@
 // tsb200_spmm_fw_host pipelines PCIe against the kernel: `mat` goes up first, then the CSR arrays
 // in row chunks; each chunk's SpMM starts as soon as its indices have landed and its output rows
 // are copied back on a second stream while later chunks are still uploading (PCIe is full duplex).
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -100,6 +101,10 @@ extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* co
 
   // chunking only pays (and only keeps out/arg_out contiguous per copy) for a single batch
   int nchunk = (B == 1 && M >= 4096 && E >= (1 << 20)) ? 8 : 1;
+  if (const char* ev = getenv("TSB200_HOST_CHUNKS")) {  // tuning knob
+    const int v = atoi(ev);
+    if (v >= 1 && v <= HostCtx::kMaxChunks && B == 1) nchunk = v;
+  }
   for (int ch = 0; ch < nchunk; ch++) {
     const int64_t r0 = M * ch / nchunk, r1 = M * (ch + 1) / nchunk;
     const int64_t e0 = rowptr_host[r0], e1 = rowptr_host[r1];

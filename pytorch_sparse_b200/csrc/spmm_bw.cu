@@ -21,36 +21,59 @@ template <> struct Vec16<float, 4> {
            __uint_as_float(a.z) * __uint_as_float(b.z) + __uint_as_float(a.w) * __uint_as_float(b.w);
   }
 };
+// bf16 / f16: sm_100 mixed-precision FMA (fma.rn.f32.{bf16,f16} -> SASS FHFMA with .H0/.H1 selectors):
+// both multiplicands straight from the packed pairs, fp32 accumulate, no unpack.
 template <> struct Vec16<__nv_bfloat16, 8> {
   static __device__ __forceinline__ float dot(const uint4& a, const uint4& b) {
     const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      s = fmaf(__uint_as_float(x[i] << 16), __uint_as_float(y[i] << 16), s);
-      s = fmaf(__uint_as_float(x[i] & 0xffff0000u), __uint_as_float(y[i] & 0xffff0000u), s);
-    }
-    return s;
+    for (int i = 0; i < 4; i++)
+      asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
+          "fma.rn.f32.bf16 %0, al, bl, %0;\n\tfma.rn.f32.bf16 %1, ah, bh, %1;\n\t}"
+          : "+f"(s0), "+f"(s1) : "r"(x[i]), "r"(y[i]));
+    return s0 + s1;
   }
 };
 template <> struct Vec16<__half, 8> {
   static __device__ __forceinline__ float dot(const uint4& a, const uint4& b) {
     const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
-    float s = 0.f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&x[i]));
-      const float2 q = __half22float2(*reinterpret_cast<const __half2*>(&y[i]));
-      s = fmaf(p.x, q.x, s);
-      s = fmaf(p.y, q.y, s);
-    }
-    return s;
+    for (int i = 0; i < 4; i++)
+      asm("{\n\t.reg .b16 al, ah, bl, bh;\n\tmov.b32 {al, ah}, %2;\n\tmov.b32 {bl, bh}, %3;\n\t"
+          "fma.rn.f32.f16 %0, al, bl, %0;\n\tfma.rn.f32.f16 %1, ah, bh, %1;\n\t}"
+          : "+f"(s0), "+f"(s1) : "r"(x[i]), "r"(y[i]));
+    return s0 + s1;
   }
 };
 
-// vector path: K*sizeof(T) % 16 == 0, 16 B aligned mat/grad.
+// Reduce U per-lane partial sums over the W*2 lanes of a lane group with a halving butterfly:
+// level l exchanges half of the values with the partner lane (xor W), so U values cost
+// U/2 + U/4 + ... + 1 + log2(LPR/U) shuffles instead of U*log2(LPR). Afterwards lane `li` of the group
+// holds the total of value index li / (LPR/U).
+template <int U, int W> __device__ __forceinline__ float multi_reduce(const float (&p)[U], int li) {
+  if constexpr (U == 1) {
+    float t = p[0];
+#pragma unroll
+    for (int off = W; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    return t;
+  } else {
+    const bool hi = (li & W) != 0;
+    float q[U / 2];
+#pragma unroll
+    for (int i = 0; i < U / 2; i++) {
+      const float send = hi ? p[i] : p[i + U / 2];
+      const float keep = hi ? p[i + U / 2] : p[i];
+      q[i] = keep + __shfl_xor_sync(0xffffffffu, send, W);
+    }
+    return multi_reduce<U / 2, W / 2>(q, li);
+  }
+}
+
+// vector path: K*sizeof(T) % 16 == 0, 16 B aligned mat/grad, M,N < 2^32.
 template <typename T, int LPR, int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 value_bw_vec_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ rowptr,
                     const int64_t* __restrict__ col, const T* __restrict__ mat,
                     const T* __restrict__ grad, T* __restrict__ out, int64_t B, int64_t M, int64_t N,
@@ -61,57 +84,72 @@ value_bw_vec_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__
   const int g = lane / LPR, li = lane % LPR;
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t nvec = K / VEC;  // 16-byte vectors per dense row
-  const int64_t row_bytes = K * (int64_t)sizeof(T);
+  const int nvec = (int)(K / VEC);  // 16-byte vectors per dense row
+  const uint32_t row_bytes = (uint32_t)(K * (int64_t)sizeof(T));
   const uint64_t pol = make_policy_evict_last();
 
-  for (int64_t e0 = wid * 32; e0 < E; e0 += nw * 32) {
-    const int64_t e = e0 + lane;
-    const bool valid = e < E;
-    const int64_t r = valid ? __ldg(row + e) : 0;
-    const int64_t c = valid ? __ldg(col + e) : 0;
-    float res = 0.f;  // lane `j` ends up with the result of nnz e0 + j
+  int64_t e0 = wid * 32;
+  // software prefetch of the next batch's (row, col): hides the index latency behind the gathers
+  uint32_t r_nxt = 0, c_nxt = 0;
+  if (e0 + lane < E) { r_nxt = (uint32_t)__ldg(row + e0 + lane); c_nxt = (uint32_t)__ldg(col + e0 + lane); }
+  for (; e0 < E; e0 += nw * 32) {
+    const uint32_t r = r_nxt, c = c_nxt;
+    const int64_t en = e0 + nw * 32 + lane;
+    if (en < E) { r_nxt = (uint32_t)__ldg(row + en); c_nxt = (uint32_t)__ldg(col + en); }
+    const int nvalid = (int)min((int64_t)32, E - e0);
+    float res = 0.f;  // lane j ends up with the result of nnz e0 + j
     for (int64_t b = 0; b < B; b++) {
-      const char* matb = (const char*)mat + b * N * row_bytes;
-      const char* gradb = (const char*)grad + b * M * row_bytes;
+      const char* matb = (const char*)mat + b * N * (int64_t)row_bytes + li * 16;
+      const char* gradb = (const char*)grad + b * M * (int64_t)row_bytes + li * 16;
 #pragma unroll 1
-      for (int s0 = 0; s0 < 32; s0 += U * G) {
+      for (int s0 = 0; s0 < nvalid; s0 += U * G) {
+        uint4 a[U], q[U];
+        bool act[U];
+        if (nvec <= LPR) {  // one vector per lane: issue every gather of the chunk before the math
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const int j = s0 + u * G + g;
+            const uint32_t rj = __shfl_sync(0xffffffffu, r, j & 31);
+            const uint32_t cj = __shfl_sync(0xffffffffu, c, j & 31);
+            act[u] = j < nvalid && li < nvec;
+            if (act[u]) {
+              a[u] = ldg128_hint(matb + (uint64_t)cj * row_bytes, pol);
+              q[u] = ldg128(gradb + (uint64_t)rj * row_bytes);
+            }
+          }
+        }
         float part[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const int j = s0 + u * G + g;  // nnz handled by this group in this step
-          const int64_t rj = __shfl_sync(0xffffffffu, r, j);
-          const int64_t cj = __shfl_sync(0xffffffffu, c, j);
-          const bool act = (e0 + j) < E;
-          float s = 0.f;
-          if (act) {
-            for (int64_t v = li; v < nvec; v += LPR) {
-              const uint4 a = ldg128_hint(matb + cj * row_bytes + v * 16, pol);
-              const uint4 q = ldg128(gradb + rj * row_bytes + v * 16);
-              s += Vec16<T, VEC>::dot(a, q);
-            }
+          const int j = s0 + u * G + g;
+          float sdot = 0.f;
+          if (nvec <= LPR) {
+            if (act[u]) sdot = Vec16<T, VEC>::dot(a[u], q[u]);
+          } else {  // rows wider than LPR vectors: strided walk
+            const uint32_t rj = __shfl_sync(0xffffffffu, r, j & 31);
+            const uint32_t cj = __shfl_sync(0xffffffffu, c, j & 31);
+            if (j < nvalid)
+              for (int v = li; v < nvec; v += LPR)
+                sdot += Vec16<T, VEC>::dot(ldg128_hint(matb + (uint64_t)cj * row_bytes + (v - li) * 16, pol),
+                                           ldg128(gradb + (uint64_t)rj * row_bytes + (v - li) * 16));
           }
-          part[u] = s;
+          part[u] = sdot;
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          float s = part[u];
-#pragma unroll
-          for (int off = LPR >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-          // group g's lanes now all hold the dot of nnz j = s0 + u*G + g; hand it to lane j
-          const int j_of_lane = lane;  // lane j wants group (j - s0 - u*G) if in range
-          const int gg = j_of_lane - s0 - u * G;
-          const float got = __shfl_sync(0xffffffffu, s, (gg >= 0 && gg < G) ? gg * LPR : 0);
-          if (gg >= 0 && gg < G) res += got;
-        }
+        // lane li of group g now gets the total of step u = li / (LPR/U); hand nnz jj = u*G + g to lane s0 + jj
+        const float tot = multi_reduce<U, LPR / 2>(part, li);
+        const int jj = lane - s0;
+        const bool mine = jj >= 0 && jj < U * G;
+        const int src = mine ? (jj % G) * LPR + (jj / G) * (LPR / U) : 0;
+        const float got = __shfl_sync(0xffffffffu, tot, src);
+        if (mine) res += got;
       }
     }
-    if (valid) {
+    if (lane < nvalid) {
       if (mean) {
         const int64_t cnt = __ldg(rowptr + r + 1) - __ldg(rowptr + r);
         res = res / (float)(cnt > 0 ? cnt : 1);
       }
-      out[e] = Traits<T>::from_acc(res);
+      out[e0 + lane] = Traits<T>::from_acc(res);
     }
   }
 }
@@ -173,7 +211,7 @@ static int launch_value_vec(const int64_t* row, const int64_t* rowptr, const int
                             const void* grad, void* out, int64_t B, int64_t M, int64_t N, int64_t K,
                             int64_t E, bool mean, cudaStream_t st) {
   int64_t blocks = (E + 255) / 256;  // 8 warps x 32 nnz per CTA pass
-  const int64_t cap = (int64_t)kNumSMs * 16;
+  const int64_t cap = (int64_t)kNumSMs * 6;  // 3 resident CTAs/SM, 2 passes
   if (blocks > cap) blocks = cap;
   value_bw_vec_kernel<T, LPR, U><<<(int)blocks, 256, 0, st>>>(row, rowptr, col, (const T*)mat, (const T*)grad,
                                                              (T*)out, B, M, N, K, E, mean);
@@ -213,7 +251,8 @@ extern "C" int tsb200_spmm_value_bw(const int64_t* row, const int64_t* rowptr, c
   const bool mean = reduce == TSB200_MEAN;
   const size_t es = dtype_size(dtype);
   const bool vec = (dtype == TSB200_F32 || dtype == TSB200_F16 || dtype == TSB200_BF16) && K > 0 &&
-                   (K * es) % 16 == 0 && !((uintptr_t)mat & 15) && !((uintptr_t)grad & 15);
+                   (K * es) % 16 == 0 && !((uintptr_t)mat & 15) && !((uintptr_t)grad & 15) &&
+                   M < ((int64_t)1 << 32) && N < ((int64_t)1 << 32) && K * (int64_t)es < ((int64_t)1 << 31);
   if (vec) {
     switch (dtype) {
       case TSB200_F32: return dispatch_value_vec<float>(row, rowptr, col, mat, grad, out, B, M, N, K, E, mean, st);

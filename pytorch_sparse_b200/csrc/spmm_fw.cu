@@ -75,12 +75,17 @@ template <typename T> struct IndexRing {
   const int64_t* col;
   const T* val;
   int64_t base;   // absolute nnz index of ring-relative 0 (multiple of 32)
-  int64_t limit;  // absolute end of valid data (E)
+  int64_t limit;  // absolute end of the range being streamed (windows past it are not fetched)
   int issued_w;   // last window issued
   int ready_w;    // windows <= ready_w are complete and visible to the whole warp
 
-  __device__ __forceinline__ void reset(int64_t base_) {
+  // start streaming a new nnz range [.., limit_): copies still in flight from the previous range
+  // (its last prefetched windows) must land before their slots are reused.
+  __device__ __forceinline__ void reset(int64_t base_, int64_t limit_) {
+    cp_async_wait<0>();
+    __syncwarp();
     base = base_;
+    limit = limit_;
     issued_w = -0x40000000;
     ready_w = -0x40000000;
   }
@@ -123,7 +128,11 @@ template <typename T> struct IndexRing {
     const int low_w = lo_rel >> 5;
     if (issued_w < need_w + kPrefetch) {
       __syncwarp();  // every lane is done reading the windows about to be overwritten
-      if (issued_w < low_w - 1) issued_w = low_w - 1;
+      if (issued_w < low_w - 1) {  // skip-ahead (deferred rows): drain before slots are reused out of order
+        cp_async_wait<0>();
+        __syncwarp();
+        issued_w = low_w - 1;
+      }
       while (issued_w < need_w + kPrefetch) issue(++issued_w, lane);
     }
     cp_async_wait<kPrefetch>();
@@ -478,7 +487,7 @@ spmm_vec_kernel(const SpmmParams p) {
     }
     __syncwarp();
 
-    ring.reset(base);
+    ring.reset(base, __shfl_sync(0xffffffffu, rp1, 31));  // lanes >= nrows hold the item's end
     const char* matb = (const char*)p.mat + b * p.N * (int64_t)row_bytes + lane_off;
     asm volatile("" : "+l"(matb));  // keep the gather base in a register
     T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0;
@@ -493,6 +502,163 @@ spmm_vec_kernel(const SpmmParams p) {
       eng.accumulate(ring, s, e, matb, row_bytes, col_ok, lane, g, pol);
       eng.reduce_groups();
       if (g == 0) eng.store_row(outb + (int64_t)rl * p.K, argb ? argb + (int64_t)rl * p.K : nullptr, e - s, p.E, col_ok, li, p.mean != 0);
+    }
+    item = __shfl_sync(0xffffffffu, next_item, 0);
+  }
+}
+
+// ---- narrow dense rows (K*sizeof(T) <= 128 B): group-per-row SUM kernel ----------------------------
+// With LPR <= 8 a row-at-a-time warp spends most of its instructions on per-row bookkeeping and on the
+// cross-group reduction (profiles/r01_ncu_spmm_f32.md: 308 warp-instructions per 16-nnz row, issue
+// slots 87 % busy). Here the G = 32/LPR lane groups of a warp each walk their OWN row: no cross-group
+// reduction, per-row overhead amortised over G rows, U independent (index -> gather) chains in flight
+// per lane. Indices are read straight from global memory (lanes of a group broadcast one address,
+// consecutive nnz hit L1). Long rows / budget overflow still go to the segment queue.
+template <typename T> __device__ __forceinline__ typename Vec<T>::vraw load_vraw(const T* p);
+template <> __device__ __forceinline__ float load_vraw<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ unsigned short load_vraw<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __ldg(reinterpret_cast<const unsigned short*>(p));
+}
+template <> __device__ __forceinline__ unsigned short load_vraw<__half>(const __half* p) {
+  return __ldg(reinterpret_cast<const unsigned short*>(p));
+}
+
+template <typename T, int LPR, int U, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
+spmm_gpr_kernel(const SpmmParams p) {
+  using V = Vec<T>;
+  using VR = typename V::vraw;
+  constexpr int VEC = V::VEC;
+  constexpr int G = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPR, li = lane % LPR;
+  const bool col_ok = p.k0 + li * VEC < p.K;
+  const uint32_t row_bytes = (uint32_t)(p.K * (int64_t)sizeof(T));
+  const int64_t lane_off = ((int64_t)p.k0 + (int64_t)li * VEC) * (int64_t)sizeof(T);
+  const uint64_t pol = make_policy_evict_last();
+  const T* __restrict__ val = (const T*)p.value;
+  const bool has_val = val != nullptr;
+
+  const int item_rows = 1 << p.item_shift;
+  const int64_t nblk = (p.M + item_rows - 1) >> p.item_shift;
+  const int64_t n_items = nblk * p.B;
+
+  unsigned int item = 0;
+  if (lane == 0) item = atomicAdd(&p.counters[0], 1u);
+  item = __shfl_sync(0xffffffffu, item, 0);
+
+  while ((int64_t)item < n_items) {
+    unsigned int next_item = 0;
+    if (lane == 0) next_item = atomicAdd(&p.counters[0], 1u);
+
+    const int64_t b = item / nblk, blk = item - b * nblk;
+    const int64_t r0 = blk << p.item_shift;
+    const int nrows = (int)min((int64_t)item_rows, p.M - r0);
+    const int64_t rp0 = __ldg(p.rowptr + r0 + min(lane, nrows));
+    const int64_t rp1 = __ldg(p.rowptr + r0 + min(lane + 1, nrows));
+    const int64_t base = __shfl_sync(0xffffffffu, rp0, 0);
+    const int s_rel = (int)(rp0 - base), e_rel = (int)(rp1 - base);
+    const int deg = e_rel - s_rel;
+
+    const bool is_long = deg > kLongT;
+    int cum = is_long ? 0 : deg;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, cum, off);
+      if (lane >= off) cum += t;
+    }
+    const bool defer = (deg > 0) && (is_long || cum > kItemCap);
+    const unsigned defer_mask = __ballot_sync(0xffffffffu, defer);
+    if (defer) {
+      const int nseg = (deg + kSeg - 1) / kSeg;
+      const unsigned seg0 = atomicAdd(&p.counters[1], (unsigned)nseg);
+      int64_t slot0 = -1;
+      if (nseg > 1) {
+        slot0 = atomicAdd(&p.counters[3], (unsigned)nseg);
+        const unsigned lr = atomicAdd(&p.counters[2], 1u);
+        if ((int64_t)lr < p.long_cap) {
+          LongRow L;
+          L.row_b = b * p.M + r0 + lane;
+          L.first_slot = slot0;
+          L.nseg_count = ((int64_t)nseg << 40) | (int64_t)deg;
+          p.longs[lr] = L;
+        }
+      }
+      for (int sgi = 0; sgi < nseg; sgi++) {
+        if ((int64_t)seg0 + sgi < p.seg_cap) {
+          Segment S;
+          S.row_b = b * p.M + r0 + lane;
+          S.start = rp0 + (int64_t)sgi * kSeg;
+          S.end = min(rp1, S.start + kSeg);
+          S.slot = slot0 < 0 ? -1 : slot0 + sgi;
+          p.segs[seg0 + sgi] = S;
+        }
+      }
+    }
+    __syncwarp();
+
+    const char* matb = (const char*)p.mat + b * p.N * (int64_t)row_bytes + lane_off;
+    asm volatile("" : "+l"(matb));
+    const int64_t* __restrict__ colb = p.col + base;
+    const T* __restrict__ valb = has_val ? val + base : nullptr;
+    T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0 + li * VEC;
+
+    for (int t = 0; t < nrows; t += G) {
+      const int rl = t + g;  // this lane group's row
+      int s = __shfl_sync(0xffffffffu, s_rel, rl & 31);
+      int e = __shfl_sync(0xffffffffu, e_rel, rl & 31);
+      const bool mine = rl < nrows && !((defer_mask >> (rl & 31)) & 1u);
+      if (!mine) e = s;
+      const int len = e - s;
+      int maxlen = len;
+#pragma unroll
+      for (int off = LPR; off < 32; off <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, off));
+
+      float acc[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; i++) acc[i] = 0.f;
+
+      // software pipeline: the (col, value) pairs of chunk k+1 are loaded while chunk k's gathers fly
+      uint32_t cn[U];
+      VR vn[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        cn[u] = 0;
+        vn[u] = V::one();
+        if (u < len) {
+          cn[u] = (uint32_t)__ldg(colb + s + u);
+          if (has_val) vn[u] = load_vraw<T>(valb + s + u);
+        }
+      }
+      for (int j0 = 0; j0 < maxlen; j0 += U) {
+        uint4 d[U];
+        VR v[U];
+        bool act[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          act[u] = (j0 + u < len) && col_ok;
+          v[u] = vn[u];
+          if (act[u]) d[u] = ldg128_hint(matb + (uint64_t)cn[u] * row_bytes, pol);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int jn = j0 + U + u;
+          if (jn < len) {
+            cn[u] = (uint32_t)__ldg(colb + s + jn);
+            if (has_val) vn[u] = load_vraw<T>(valb + s + jn);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (act[u]) V::fma(acc, v[u], d[u]);
+      }
+      if (mine && col_ok) {
+        if (p.mean) {
+#pragma unroll
+          for (int i = 0; i < VEC; i++) acc[i] = acc[i] / (float)(len > 0 ? len : 1);
+        }
+        stg128_stream(outb + (int64_t)rl * p.K, V::pack(acc));
+      }
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
   }
@@ -535,7 +701,7 @@ spmm_seg_kernel(const SpmmParams p) {
     const Segment S = p.segs[sidx];
     const int64_t b = S.row_b / p.M, row = S.row_b - b * p.M;
     const int64_t base = S.start & ~(int64_t)31;
-    ring.reset(base);
+    ring.reset(base, S.end);
     const char* matb = (const char*)p.mat + b * p.N * (int64_t)row_bytes + lane_off;
     asm volatile("" : "+l"(matb));
     Eng eng;
@@ -693,12 +859,15 @@ static int grid_for(const void* kernel, int threads) {
   return per_sm * sms;
 }
 
-template <typename T, int RED, int LPR, int CH, int U, int MINB = 1>
+template <typename T, int RED, int LPR, int CH, int U, int MINB = 1, bool GPR = false>
 static int launch_vec(SpmmParams p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int kcols = LPR * CH * VEC;
-  auto* kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB>;
-  auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, U, MINB>;
+  void (*kmain)(const SpmmParams);
+  if constexpr (GPR) kmain = spmm_gpr_kernel<T, LPR, U, MINB>;
+  else kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB>;
+  constexpr int USEG = (U > LPR) ? LPR : U;  // the row engine needs U * (32 / LPR) <= 32
+  auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, USEG, MINB>;
   static int grid_main = 0, grid_seg = 0;  // per-instantiation cache
   if (!grid_main) grid_main = grid_for((const void*)kmain, kWarpsPerCta * 32);
   if (!grid_seg) grid_seg = grid_for((const void*)kseg, kWarpsPerCta * 32);
@@ -727,6 +896,12 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
 template <typename T, int RED> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   const int64_t vecs = p.K / VEC;  // 16-byte vectors per dense row
+  if constexpr (RED == R_SUM) {  // narrow rows: group-per-row kernel (sum / mean)
+    if (vecs <= 1) return launch_vec<T, RED, 1, 1, 4, 5, true>(p, st);
+    if (vecs <= 2) return launch_vec<T, RED, 2, 1, 4, 5, true>(p, st);
+    if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4, 5, true>(p, st);
+    if (vecs <= 8) return launch_vec<T, RED, 8, 1, 4, 5, true>(p, st);
+  }
   if (vecs <= 1) return launch_vec<T, RED, 1, 1, 1, 6>(p, st);
   if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4, 5>(p, st);
   if (vecs <= 8) return launch_vec<T, RED, 8, 1, 4, 5>(p, st);

@@ -64,6 +64,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
   return r;
 }
 
+// Per output row the CTA first stages the A-row metadata in shared memory — for each a_ik: start and
+// length of row k of B, a_ik itself, and the exclusive prefix of the lengths — so that the row's
+// products form ONE flat index space [0, P). Every later pass walks p = tid, tid+256, ... and finds
+// its (a_ik, b_kj) by a binary search in the prefix (<= 8 shared-memory steps): all global loads of
+// a pass are independent, i.e. one DRAM/L2 latency per pass instead of one per A entry.
+constexpr int kABatch = kSpThreads;  // A entries staged per batch
+
 template <bool NUMERIC, typename T>
 __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -77,9 +84,11 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
   __shared__ int s_warp[kSpThreads / 32];
   __shared__ unsigned int s_row;
   __shared__ long long s_min, s_max;
+  __shared__ int64_t s_bs[kABatch];
+  __shared__ int s_off[kABatch + 1];
+  __shared__ T s_av[NUMERIC ? kABatch : 1];
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NWARP = kSpThreads / 32;
+  const int tid = threadIdx.x;
   for (int i = tid; i < WW + NSW; i += kSpThreads) bitmap[i] = 0;  // summary is contiguous after bitmap
   __syncthreads();
 
@@ -97,6 +106,7 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
     const int64_t a_s = p.rowptr_a[i], a_e = p.rowptr_a[i + 1];
     int64_t win_lo = 0, win_hi = 0;  // window index range [win_lo, win_hi]
     if (multi_window) {
+      // B rows are column-sorted (SparseStorage invariant): first/last entry bound the row's columns
       if (tid == 0) { s_min = 0x7fffffffffffffffLL; s_max = -1; }
       __syncthreads();
       long long mn = 0x7fffffffffffffffLL, mx = -1;
@@ -119,20 +129,36 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
 
     for (int64_t win = win_lo; win <= win_hi; win++) {
       const int64_t wlo = win * W, whi = wlo + W;
-      // ---- mark ----
-      for (int64_t a = a_s + warp; a < a_e; a += NWARP) {
-        const int64_t k = p.col_a[a];
-        const int64_t bs = p.rowptr_b[k], be = p.rowptr_b[k + 1];
-        for (int64_t f = bs + lane; f < be; f += 32) {
-          const int64_t c = p.col_b[f];
+      // ---- mark: batches of <= 256 A entries, flat product walk ----
+      for (int64_t ab = a_s; ab < a_e; ab += kABatch) {
+        const int na = (int)min((int64_t)kABatch, a_e - ab);
+        int len = 0;
+        if (tid < na) {
+          const int64_t k = p.col_a[ab + tid];
+          const int64_t bs = p.rowptr_b[k];
+          len = (int)(p.rowptr_b[k + 1] - bs);
+          s_bs[tid] = bs;
+        }
+        int P;
+        const int off = block_exclusive_scan(len, s_warp, P);
+        s_off[tid] = off;
+        if (tid == 0) s_off[kABatch] = P;
+        __syncthreads();
+        for (int q = tid; q < P; q += kSpThreads) {
+          int lo = 0, hi = na;  // largest e with s_off[e] <= q
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= q) lo = mid; else hi = mid;
+          }
+          const int64_t c = p.col_b[s_bs[lo] + (q - s_off[lo])];
           if (c >= wlo && c < whi) {
             const uint32_t cc = (uint32_t)(c - wlo);
             const uint32_t old = atomicOr(&bitmap[cc >> 5], 1u << (cc & 31));
             if (old == 0) atomicOr(&summary[cc >> 10], 1u << ((cc >> 5) & 31));
           }
         }
+        __syncthreads();
       }
-      __syncthreads();
 
       if (!NUMERIC) {
         int cnt = 0;
@@ -200,26 +226,41 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
             }
           }
         }
-        // ---- accumulate values at their rank ----
+        // ---- accumulate values at their rank (flat product walk again) ----
         if (p.val_c) {
-          if (!use_smem_acc) __threadfence_block();
-          for (int64_t a = a_s + warp; a < a_e; a += NWARP) {
-            const int64_t k = p.col_a[a];
-            const T av = va ? va[a] : (T)1;
-            const int64_t bs = p.rowptr_b[k], be = p.rowptr_b[k + 1];
-            for (int64_t f = bs + lane; f < be; f += 32) {
+          for (int64_t ab = a_s; ab < a_e; ab += kABatch) {
+            const int na = (int)min((int64_t)kABatch, a_e - ab);
+            int len = 0;
+            if (tid < na) {
+              const int64_t k = p.col_a[ab + tid];
+              const int64_t bs = p.rowptr_b[k];
+              len = (int)(p.rowptr_b[k + 1] - bs);
+              s_bs[tid] = bs;
+              s_av[tid] = va ? va[ab + tid] : (T)1;
+            }
+            int P;
+            const int off2 = block_exclusive_scan(len, s_warp, P);
+            s_off[tid] = off2;
+            __syncthreads();
+            for (int q = tid; q < P; q += kSpThreads) {
+              int lo = 0, hi = na;
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= q) lo = mid; else hi = mid;
+              }
+              const int64_t f = s_bs[lo] + (q - s_off[lo]);
               const int64_t c = p.col_b[f];
               if (c >= wlo && c < whi) {
                 const uint32_t cc = (uint32_t)(c - wlo);
                 const uint32_t w = cc >> 5;
                 const int rank = base[w >> 5] + pre16[w] + __popc(bitmap[w] & ((1u << (cc & 31)) - 1u));
-                const T pv = av * (vb ? vb[f] : (T)1);
+                const T pv = s_av[lo] * (vb ? vb[f] : (T)1);
                 if (use_smem_acc) atomicAdd(&acc[rank], pv);
                 else atomicAdd(((T*)p.val_c) + obase + rank, pv);
               }
             }
+            __syncthreads();
           }
-          __syncthreads();
           if (use_smem_acc) for (int q = tid; q < wc; q += kSpThreads) ((T*)p.val_c)[obase + q] = acc[q];
         }
         __syncthreads();

@@ -36,6 +36,21 @@ if "pcie" in which:
     ms_dn = timeit(lambda: h.copy_(d, non_blocking=True), 5, 1)
     out(what="pcie_pinned_256MB", h2d_gbs=256 / 1024 / ms_up * 1e3, d2h_gbs=256 / 1024 / ms_dn * 1e3)
 
+if "e2e" in which:
+    M = 1_000_000; F = 128
+    row, rowptr, col = fast_random_csr(M, M, 16, 1, dev)
+    val = (torch.rand(col.numel(), device=dev) + 0.5).bfloat16()
+    x = torch.randn(M, F, device=dev).bfloat16()
+    rp_h, col_h, val_h, x_h = [t.cpu().pin_memory() for t in (rowptr, col, val, x)]
+    for _ in range(2):
+        ops.spmm_fw_host(rp_h, col_h, val_h, x_h, "sum")
+    t0 = time.perf_counter()
+    for _ in range(5):
+        o, _ = ops.spmm_fw_host(rp_h, col_h, val_h, x_h, "sum")
+    ms = (time.perf_counter() - t0) * 1e3 / 5
+    import os
+    out(what="e2e_host_c2", chunks=os.environ.get("TSB200_HOST_CHUNKS", "default"), ms=ms)
+
 if "c2bw" in which:  # SpMM_sum fwd+bwd at C2 (value grad + dense grad)
     M = 1_000_000; F = 128
     row, rowptr, col = fast_random_csr(M, M, 16, 1, dev)
