@@ -64,11 +64,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
   return r;
 }
 
-// Per output row the CTA first stages the A-row metadata in shared memory — for each a_ik: start and
-// length of row k of B, a_ik itself, and the exclusive prefix of the lengths — so that the row's
-// products form ONE flat index space [0, P). Every later pass walks p = tid, tid+256, ... and finds
-// its (a_ik, b_kj) by a binary search in the prefix (<= 8 shared-memory steps): all global loads of
-// a pass are independent, i.e. one DRAM/L2 latency per pass instead of one per A entry.
+// Per output row the CTA first stages the A-row metadata in shared memory (for each a_ik: start and
+// length of row k of B, and a_ik), ONCE; the product walks (mark, accumulate) then run warp-per-A-entry
+// with lanes striding the B row: the only global loads of a walk are the independent, coalesced reads
+// of B's column (and value) arrays — one L2/DRAM latency per walk instead of one per A entry.
 constexpr int kABatch = kSpThreads;  // A entries staged per batch
 
 template <bool NUMERIC, typename T>
@@ -85,10 +84,11 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
   __shared__ unsigned int s_row;
   __shared__ long long s_min, s_max;
   __shared__ int64_t s_bs[kABatch];
-  __shared__ int s_off[kABatch + 1];
+  __shared__ int s_len[kABatch];
   __shared__ T s_av[NUMERIC ? kABatch : 1];
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = kSpThreads / 32;
   for (int i = tid; i < WW + NSW; i += kSpThreads) bitmap[i] = 0;  // summary is contiguous after bitmap
   __syncthreads();
 
@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
     if (tid == 0) s_row = atomicAdd(p.counter, 1u);
     __syncthreads();
     const int64_t i = s_row;
+    const int64_t a_s = p.rowptr_a[i < p.M ? i : 0], a_e = p.rowptr_a[i < p.M ? i + 1 : 0];
     __syncthreads();
     if (i >= p.M) break;
-    const int64_t a_s = p.rowptr_a[i], a_e = p.rowptr_a[i + 1];
     int64_t win_lo = 0, win_hi = 0;  // window index range [win_lo, win_hi]
     if (multi_window) {
       // B rows are column-sorted (SparseStorage invariant): first/last entry bound the row's columns
@@ -124,37 +124,37 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
       else { win_lo = s_min / W; win_hi = s_max / W; }
       __syncthreads();
     }
+    const bool single_batch = (a_e - a_s) <= kABatch;
     int64_t done = 0;  // nnz of this row emitted by previous windows
     const int64_t out0 = NUMERIC ? p.rowptr_c[i] : 0;
+    bool staged = false;
 
     for (int64_t win = win_lo; win <= win_hi; win++) {
       const int64_t wlo = win * W, whi = wlo + W;
-      // ---- mark: batches of <= 256 A entries, flat product walk ----
+      // ---- mark ----
       for (int64_t ab = a_s; ab < a_e; ab += kABatch) {
         const int na = (int)min((int64_t)kABatch, a_e - ab);
-        int len = 0;
-        if (tid < na) {
-          const int64_t k = p.col_a[ab + tid];
-          const int64_t bs = p.rowptr_b[k];
-          len = (int)(p.rowptr_b[k + 1] - bs);
-          s_bs[tid] = bs;
-        }
-        int P;
-        const int off = block_exclusive_scan(len, s_warp, P);
-        s_off[tid] = off;
-        if (tid == 0) s_off[kABatch] = P;
-        __syncthreads();
-        for (int q = tid; q < P; q += kSpThreads) {
-          int lo = 0, hi = na;  // largest e with s_off[e] <= q
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_off[mid] <= q) lo = mid; else hi = mid;
+        if (!(single_batch && staged)) {
+          if (tid < na) {
+            const int64_t k = p.col_a[ab + tid];
+            const int64_t bs = p.rowptr_b[k];
+            s_bs[tid] = bs;
+            s_len[tid] = (int)(p.rowptr_b[k + 1] - bs);
+            if (NUMERIC) s_av[tid] = va ? va[ab + tid] : (T)1;
           }
-          const int64_t c = p.col_b[s_bs[lo] + (q - s_off[lo])];
-          if (c >= wlo && c < whi) {
-            const uint32_t cc = (uint32_t)(c - wlo);
-            const uint32_t old = atomicOr(&bitmap[cc >> 5], 1u << (cc & 31));
-            if (old == 0) atomicOr(&summary[cc >> 10], 1u << ((cc >> 5) & 31));
+          __syncthreads();
+          staged = true;
+        }
+        for (int e = warp; e < na; e += NWARP) {
+          const int64_t bs = s_bs[e];
+          const int len = s_len[e];
+          for (int f = lane; f < len; f += 32) {
+            const int64_t c = p.col_b[bs + f];
+            if (c >= wlo && c < whi) {
+              const uint32_t cc = (uint32_t)(c - wlo);
+              const uint32_t old = atomicOr(&bitmap[cc >> 5], 1u << (cc & 31));
+              if (old == 0) atomicOr(&summary[cc >> 10], 1u << ((cc >> 5) & 31));
+            }
           }
         }
         __syncthreads();
@@ -226,44 +226,43 @@ __global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
             }
           }
         }
-        // ---- accumulate values at their rank (flat product walk again) ----
+        // ---- accumulate values at their rank ----
         if (p.val_c) {
           for (int64_t ab = a_s; ab < a_e; ab += kABatch) {
             const int na = (int)min((int64_t)kABatch, a_e - ab);
-            int len = 0;
-            if (tid < na) {
-              const int64_t k = p.col_a[ab + tid];
-              const int64_t bs = p.rowptr_b[k];
-              len = (int)(p.rowptr_b[k + 1] - bs);
-              s_bs[tid] = bs;
-              s_av[tid] = va ? va[ab + tid] : (T)1;
-            }
-            int P;
-            const int off2 = block_exclusive_scan(len, s_warp, P);
-            s_off[tid] = off2;
-            __syncthreads();
-            for (int q = tid; q < P; q += kSpThreads) {
-              int lo = 0, hi = na;
-              while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_off[mid] <= q) lo = mid; else hi = mid;
+            if (!single_batch) {
+              __syncthreads();
+              if (tid < na) {
+                const int64_t k = p.col_a[ab + tid];
+                const int64_t bs = p.rowptr_b[k];
+                s_bs[tid] = bs;
+                s_len[tid] = (int)(p.rowptr_b[k + 1] - bs);
+                s_av[tid] = va ? va[ab + tid] : (T)1;
               }
-              const int64_t f = s_bs[lo] + (q - s_off[lo]);
-              const int64_t c = p.col_b[f];
-              if (c >= wlo && c < whi) {
-                const uint32_t cc = (uint32_t)(c - wlo);
-                const uint32_t w = cc >> 5;
-                const int rank = base[w >> 5] + pre16[w] + __popc(bitmap[w] & ((1u << (cc & 31)) - 1u));
-                const T pv = s_av[lo] * (vb ? vb[f] : (T)1);
-                if (use_smem_acc) atomicAdd(&acc[rank], pv);
-                else atomicAdd(((T*)p.val_c) + obase + rank, pv);
+              __syncthreads();
+            }
+            for (int e = warp; e < na; e += NWARP) {
+              const int64_t bs = s_bs[e];
+              const int len = s_len[e];
+              const T av = s_av[e];
+              for (int f = lane; f < len; f += 32) {
+                const int64_t c = p.col_b[bs + f];
+                if (c >= wlo && c < whi) {
+                  const uint32_t cc = (uint32_t)(c - wlo);
+                  const uint32_t w = cc >> 5;
+                  const int rank = base[w >> 5] + pre16[w] + __popc(bitmap[w] & ((1u << (cc & 31)) - 1u));
+                  const T pv = av * (vb ? vb[bs + f] : (T)1);
+                  if (use_smem_acc) atomicAdd(&acc[rank], pv);
+                  else atomicAdd(((T*)p.val_c) + obase + rank, pv);
+                }
               }
             }
-            __syncthreads();
           }
+          __syncthreads();
           if (use_smem_acc) for (int q = tid; q < wc; q += kSpThreads) ((T*)p.val_c)[obase + q] = acc[q];
+        } else {
+          __syncthreads();
         }
-        __syncthreads();
         // ---- clear touched words ----
         for (int sw = tid; sw < NSW; sw += kSpThreads) {
           uint32_t m = summary[sw];
