@@ -1,6 +1,9 @@
 """Build libtsb200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-    python -m pytorch_sparse_b200.build [--force] [--verbose]
+    python build_native.py [--force] [--verbose]
+
+Stand-alone on purpose (it lives outside the package): importing `pytorch_sparse_b200` requires the
+library to exist, so the build step must not import it.
 
 No torch headers are involved: the library is plain CUDA C++ behind `include/tsb200.h`.
 Objects are cached next to the sources (`csrc/_build/`) keyed on source + header mtimes and flags.
@@ -15,9 +18,10 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
-PKG = Path(__file__).resolve().parent
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / "pytorch_sparse_b200"
 CSRC = PKG / "csrc"
-INCLUDE = PKG.parent / "include"
+INCLUDE = ROOT / "include"
 BUILD = CSRC / "_build"
 LIB = PKG / "libtsb200.so"
 

@@ -133,6 +133,16 @@ TSB200_API int tsb200_csr2csc(const int64_t* row, const int64_t* col, int64_t E,
                    size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Segment reduce over a CSR pointer.  Replaces torch_scatter.segment_csr / scatter as called by the row and
+ *   column reductions of torch_sparse/reduce.py:36-54 (`segment_csr(value, rowptr, None, reduce)` for dim=1,
+ *   `scatter(value, col, 0, None, N, reduce)` for dim=0, which on the CSC view is a segment reduce over colptr).
+ *   out[s, d] = reduce_{j in [ptr[s], ptr[s+1])} value[perm ? perm[j] : j, d];  empty segment -> 0.
+ *   ptr i64[S+1]; perm i64[E] or NULL; value dtype[E, D]; out dtype[S, D]; reduce in {SUM, MEAN, MIN, MAX}.
+ * ------------------------------------------------------------------------------------------ */
+TSB200_API int tsb200_segment_reduce(const int64_t* ptr, const int64_t* perm, const void* value, void* out,
+                                     int64_t S, int64_t D, int dtype, int reduce, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * COO coalesce.  Replaces torch_sparse.coalesce -> SparseStorage.__init__ sort + .coalesce()
  *   (torch_sparse/coalesce.py:5-25, torch_sparse/storage.py:149-162, 436-466).
  *   Phase 1 (tsb200_coalesce_sort): key = row*N + col, stable radix sort with the original position

@@ -188,6 +188,44 @@ def main():
     back = torch.ops.torch_sparse.ptr2ind(ptr, ind.numel())
     torch.save({"meta": meta, "ind": ind, "M": 1200, "ptr": ptr, "ind_back": back}, GOLD / "convert.pt")
 
+    # ---- (h) SURVEY §8(f) "next" rows: reductions (reduce.py), sparse add (add.py / spadd.py), narrow (narrow.py) ----
+    import torch_sparse as tsr
+    g = torch.Generator().manual_seed(61)
+    M, N = 40, 30
+    ra, ca = random_structure(M, N, 5, seed=62, empty_rows=(0, 7))
+    rb, cb = random_structure(M, N, 4, seed=63, empty_rows=(3,))
+    va = torch.randn(ra.numel(), generator=g, dtype=torch.float64)
+    vb = torch.randn(rb.numel(), generator=g, dtype=torch.float64)
+    va2 = torch.randn(ra.numel(), 3, generator=g, dtype=torch.float64)
+    A = SparseTensor(row=ra, col=ca, value=va, sparse_sizes=(M, N))
+    A2 = SparseTensor(row=ra, col=ca, value=va2, sparse_sizes=(M, N))
+    A0 = SparseTensor(row=ra, col=ca, sparse_sizes=(M, N))
+    Bm = SparseTensor(row=rb, col=cb, value=vb, sparse_sizes=(M, N))
+    red = {}
+    for name, T in (("v", A), ("v2", A2), ("nv", A0)):
+        for op in ("sum", "mean", "min", "max"):
+            for dim in (None, 0, 1, -1):
+                if name == "nv" and dim == -1:
+                    dim_eff = 1
+                else:
+                    dim_eff = dim
+                try:
+                    red[f"{name}_{op}_{dim}"] = getattr(tsr, op)(T, dim_eff)
+                except Exception as e:  # shape/dtype corner the reference itself rejects
+                    red[f"{name}_{op}_{dim}"] = None
+    C = A.add(Bm) if hasattr(A, "add") else tsr.add(A, Bm)
+    si, sv = tsr.spadd(torch.stack([ra, ca]), va, torch.stack([rb, cb]), vb, M, N)
+    n0 = tsr.narrow(A, 0, 5, 20)
+    n1 = tsr.narrow(A, 1, 4, 15)
+    torch.save({"meta": meta,
+                "in": dict(ra=ra, ca=ca, va=va, va2=va2, rb=rb, cb=cb, vb=vb, M=M, N=N),
+                "reduce": red,
+                "add": dict(row=C.storage.row(), col=C.storage.col(), value=C.storage.value()),
+                "spadd": dict(index=si, value=sv),
+                "narrow0": dict(rowptr=n0.storage.rowptr(), col=n0.storage.col(), value=n0.storage.value(), sizes=n0.sparse_sizes()),
+                "narrow1": dict(row=n1.storage.row(), col=n1.storage.col(), value=n1.storage.value(), sizes=n1.sparse_sizes())},
+               GOLD / "next_rows.pt")
+
     sizes = {p.name: p.stat().st_size for p in sorted(GOLD.glob("*.pt"))}
     print("wrote", sizes, "total", sum(sizes.values()))
 

@@ -37,6 +37,7 @@ SIGNATURES = {
     "tsb200_coalesce_emit": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tsb200_coalesce_perm": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
+    "tsb200_segment_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "tsb200_spspmm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64]),
     "tsb200_spspmm_symbolic": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                        c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
@@ -56,7 +57,7 @@ def _load() -> ctypes.CDLL:
     if not LIB_PATH.exists():
         raise ImportError(
             f"pytorch_sparse_b200: {LIB_PATH} is missing. Build it with "
-            f"`python -m pytorch_sparse_b200.build` (needs nvcc, sm_100a). There is no fallback path.")
+            f"`python build_native.py` (needs nvcc, sm_100a). There is no fallback path.")
     try:
         lib = ctypes.CDLL(str(LIB_PATH), mode=ctypes.RTLD_GLOBAL)
     except OSError as e:  # pragma: no cover

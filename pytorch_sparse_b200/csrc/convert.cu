@@ -91,6 +91,47 @@ __global__ void colptr_kernel(const uint32_t* __restrict__ sorted_col, int64_t E
   }
 }
 
+// warp per segment, lanes stride the segment's entries, shuffle tree combine (sum in acc_t, in lane order).
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_reduce_kernel(const int64_t* __restrict__ ptr, const int64_t* __restrict__ perm, const T* __restrict__ value,
+                      T* __restrict__ out, int64_t S, int64_t D, int reduce) {
+  using acc_t = typename Traits<T>::acc_t;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t seg = wid; seg < S; seg += nw) {
+    const int64_t b = __ldg(ptr + seg), e = __ldg(ptr + seg + 1);
+    for (int64_t d = 0; d < D; d++) {
+      acc_t a = (acc_t)0;
+      bool have = false;
+      for (int64_t j = b + lane; j < e; j += 32) {
+        const int64_t src = perm ? __ldg(perm + j) : j;
+        const acc_t v = Traits<T>::to_acc(value[src * D + d]);
+        if (!have) { a = v; have = true; }
+        else if (reduce == TSB200_SUM || reduce == TSB200_MEAN) a = a + v;
+        else if (reduce == TSB200_MIN) a = v < a ? v : a;
+        else a = v > a ? v : a;
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const acc_t o = __shfl_down_sync(0xffffffffu, a, off);
+        const bool oh = __shfl_down_sync(0xffffffffu, (int)have, off) != 0;
+        if (oh) {
+          if (!have) { a = o; have = true; }
+          else if (reduce == TSB200_SUM || reduce == TSB200_MEAN) a = a + o;
+          else if (reduce == TSB200_MIN) a = o < a ? o : a;
+          else a = o > a ? o : a;
+        }
+      }
+      if (lane == 0) {
+        if (reduce == TSB200_MEAN && e > b) a = a / (acc_t)(e - b);
+        out[seg * D + d] = Traits<T>::from_acc(have ? a : (acc_t)0);
+      }
+    }
+  }
+}
+
 static inline int grid1d(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = (int64_t)kNumSMs * 32;
@@ -181,4 +222,18 @@ extern "C" int tsb200_csr2csc(const int64_t* row, const int64_t* col, int64_t E,
     TSB_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int tsb200_segment_reduce(const int64_t* ptr, const int64_t* perm, const void* value, void* out, int64_t S,
+                                     int64_t D, int dtype, int reduce, void* stream) {
+  if (S < 0 || D < 0 || reduce < TSB200_SUM || reduce > TSB200_MAX) return TSB200_ERR_INVALID_ARG;
+  if (S == 0 || D == 0) return 0;
+  if (!ptr || !out) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dispatch_dtype(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    segment_reduce_kernel<T><<<grid1d(S * 32, 256), 256, 0, st>>>(ptr, perm, (const T*)value, (T*)out, S, D, reduce);
+    TSB_LAUNCH_CHECK();
+    return 0;
+  });
 }

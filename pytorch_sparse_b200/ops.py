@@ -219,6 +219,27 @@ def csr2csc(row: Tensor, col: Tensor, M: int, N: int, want_colptr: bool = True,
     return perm, colptr, row_csc
 
 
+def segment_reduce(ptr: Tensor, value: Tensor, reduce: str = "sum", perm: Optional[Tensor] = None) -> Tensor:
+    """out[s] = reduce(value[perm?][ptr[s]:ptr[s+1]]) along dim 0, empty segments -> 0
+    (torch_scatter.segment_csr as used by torch_sparse/reduce.py:36-54)."""
+    _check_cuda(ptr, "ptr")
+    _check_cuda(value, "value")
+    ptr = _i64(ptr, "ptr")
+    value = value.contiguous()
+    S = ptr.numel() - 1
+    E = value.size(0)
+    D = value.numel() // E if E > 0 else int(torch.Size(value.shape[1:]).numel())
+    out = torch.zeros((S,) + tuple(value.shape[1:]), dtype=value.dtype, device=value.device)
+    if S == 0 or D == 0 or E == 0:
+        return out
+    if perm is not None:
+        perm = _i64(perm, "perm")
+    with torch.cuda.device(value.device):
+        check(lib.tsb200_segment_reduce(_p(ptr), _p(perm), _p(value), _p(out), S, D, _dtype_code(value.dtype),
+                                        _reduce_code(reduce), _stream(value.device)), "tsb200_segment_reduce")
+    return out
+
+
 class _PinnedScalar:
     """One pinned int64 per device-side count read back from the GPU (E', nnz(C))."""
 

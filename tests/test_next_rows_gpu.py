@@ -1,0 +1,82 @@
+"""SURVEY §8(f) "next" rows on the GPU vs golden vectors from the unmodified reference: row/column
+reductions (torch_sparse/reduce.py), sparse + sparse (add.py:38-56, spadd.py:5-18), narrow (narrow.py)."""
+from pathlib import Path
+
+import pytest
+import torch
+
+import pytorch_sparse_b200 as ts
+from pytorch_sparse_b200 import ops
+from util import random_csr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+D = torch.load(Path(__file__).resolve().parent / "golden" / "next_rows.pt", weights_only=False)
+
+
+def _mk(kind):
+    i = D["in"]
+    v = {"v": i["va"], "v2": i["va2"], "nv": None}[kind]
+    return ts.SparseTensor(row=i["ra"].to(DEV), col=i["ca"].to(DEV), value=None if v is None else v.to(DEV),
+                           sparse_sizes=(i["M"], i["N"]))
+
+
+@pytest.mark.parametrize("kind", ["v", "v2", "nv"])
+def test_reductions_vs_reference(kind):
+    a = _mk(kind)
+    for op in ("sum", "mean", "min", "max"):
+        for dim in (None, 0, 1, -1):
+            ref = D["reduce"][f"{kind}_{op}_{dim}"]
+            if ref is None:
+                continue
+            dim_eff = 1 if (kind == "nv" and dim == -1) else dim
+            got = getattr(ts, op)(a, dim_eff)
+            assert got.shape == ref.shape, (kind, op, dim)
+            if op in ("min", "max"):
+                assert torch.equal(got.cpu().to(ref.dtype), ref), (kind, op, dim)
+            else:
+                assert torch.allclose(got.cpu().to(ref.dtype), ref, rtol=1e-12, atol=1e-12), (kind, op, dim)
+
+
+def test_add_spadd_narrow_vs_reference():
+    i = D["in"]
+    a = _mk("v")
+    b = ts.SparseTensor(row=i["rb"].to(DEV), col=i["cb"].to(DEV), value=i["vb"].to(DEV), sparse_sizes=(i["M"], i["N"]))
+    c = a + b
+    assert torch.equal(c.storage.row().cpu(), D["add"]["row"]) and torch.equal(c.storage.col().cpu(), D["add"]["col"])
+    assert torch.allclose(c.storage.value().cpu(), D["add"]["value"], rtol=1e-12, atol=1e-12)
+    idx, v = ts.spadd(torch.stack([i["ra"], i["ca"]]).to(DEV), i["va"].to(DEV), torch.stack([i["rb"], i["cb"]]).to(DEV),
+                      i["vb"].to(DEV), i["M"], i["N"])
+    assert torch.equal(idx.cpu(), D["spadd"]["index"])
+    assert torch.allclose(v.cpu(), D["spadd"]["value"], rtol=1e-12, atol=1e-12)
+    n0 = ts.narrow(a, 0, 5, 20)
+    assert n0.sparse_sizes() == tuple(D["narrow0"]["sizes"])
+    assert torch.equal(n0.storage.rowptr().cpu(), D["narrow0"]["rowptr"]) and torch.equal(n0.storage.col().cpu(), D["narrow0"]["col"])
+    assert torch.equal(n0.storage.value().cpu(), D["narrow0"]["value"])
+    n1 = ts.narrow(a, 1, 4, 15)
+    assert n1.sparse_sizes() == tuple(D["narrow1"]["sizes"])
+    assert torch.equal(n1.storage.row().cpu(), D["narrow1"]["row"]) and torch.equal(n1.storage.col().cpu(), D["narrow1"]["col"])
+    assert torch.equal(n1.storage.value().cpu(), D["narrow1"]["value"])
+    # row slice feeds SpMM directly (the multi-GPU partitioner)
+    x = torch.randn(i["N"], 8, device=DEV, dtype=torch.float64)
+    assert torch.allclose(n0 @ x, (a @ x)[5:25], atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.int64])
+@pytest.mark.parametrize("reduce", ["sum", "mean", "min", "max"])
+def test_segment_reduce_vs_oracle(oracle, dtype, reduce):
+    row, rowptr, col = random_csr(300, 200, 9, seed=3, power_law=True, empty_rows=(0, 5, 299), long_rows=[(7, 190)])
+    g = torch.Generator().manual_seed(1)
+    v = torch.randn(col.numel(), 2, generator=g)
+    v = (v * 10).round().to(dtype) if dtype == torch.int64 else v.to(dtype)
+    out = ops.segment_reduce(rowptr.to(DEV), v.to(DEV), reduce)
+    ref = oracle.segment_reduce(rowptr, v, reduce)
+    if dtype == torch.int64 or reduce in ("min", "max"):
+        assert torch.equal(out.cpu(), ref)
+    else:  # warp-tree summation order differs from the sequential oracle
+        tol = 1e-5 if dtype == torch.float32 else 1e-12
+        assert torch.allclose(out.cpu(), ref, rtol=tol, atol=tol * 50)
+    perm = torch.randperm(col.numel(), generator=g)
+    out_p = ops.segment_reduce(rowptr.to(DEV), v.to(DEV), reduce, perm=perm.to(DEV))
+    ref_p = oracle.segment_reduce(rowptr, v, reduce, perm=perm)
+    assert torch.allclose(out_p.cpu().double(), ref_p.double(), rtol=1e-5, atol=1e-3)
