@@ -225,3 +225,44 @@ def test_full_size_properties():
     a = am[pick]
     prod = (value[a].float() * x[col[a], k.unsqueeze(0).expand_as(a)].float()).bfloat16()
     assert torch.equal(prod, ym[pick])
+
+
+def test_full_size_c2_vs_oracle(oracle):
+    """BASELINE configs[1] at FULL size, directly against the oracle (fp32 restatement on the bf16
+    inputs, OpenMP over rows): every one of the 128M outputs within 1e-2 of the |A||B| bound, and the
+    fp32 kernel within 1e-5."""
+    import bench
+    w = bench.WORKLOADS["c2"]
+    rowptr, col, value, N = bench.gen_matrix(w, 0, 1)
+    x = bench.gen_dense(w, 0, N)
+    vb, xb = value.bfloat16(), x.bfloat16()
+    ref, _ = oracle.spmm(rowptr, col, vb.float(), xb.float(), "sum")          # exact products, fp32 sums
+    bound, _ = oracle.spmm(rowptr, col, vb.float().abs(), xb.float().abs(), "sum")
+    bound.clamp_(min=1e-20)
+    d = [t.to(DEV) for t in (rowptr, col)]
+    out_bf16, _ = ops.spmm_fw(d[0], d[1], vb.to(DEV), xb.to(DEV), "sum")
+    err = ((out_bf16.cpu().float() - ref).abs() / bound).max().item()
+    assert err <= 1e-2, err
+    out_f32, _ = ops.spmm_fw(d[0], d[1], vb.float().to(DEV), xb.float().to(DEV), "sum")
+    err32 = ((out_f32.cpu() - ref).abs() / bound).max().item()
+    assert err32 <= 1e-5, err32
+
+
+def test_full_size_c3_max_vs_oracle(oracle):
+    """BASELINE configs[2] at FULL size (500k x 500k power-law, F=256 fp32, max): values and arg_out
+    BIT-EXACT against the oracle, including the rows split into segments and the empty rows."""
+    import bench
+    w = bench.WORKLOADS["c3"]
+    rowptr, col, value, N = bench.gen_matrix(w, 0, 1)
+    x = bench.gen_dense(w, 0, N)
+    ref, rarg = oracle.spmm(rowptr, col, value, x, "max")
+    out, arg = ops.spmm_fw(rowptr.to(DEV), col.to(DEV), value.to(DEV), x.to(DEV), "max")
+    assert torch.equal(arg.cpu(), rarg)
+    assert torch.equal(out.cpu(), ref)
+    # backward through the fused min/max kernel vs the oracle's restatement of the ATen chain
+    g = torch.Generator().manual_seed(3)
+    go = torch.randn(w["M"], w["F"], generator=g)
+    gv, gm = ops.spmm_minmax_bw(col.to(DEV), value.to(DEV), x.to(DEV), go.to(DEV), arg, True, True)
+    rv, rm = oracle.spmm_minmax_bw(col, value.double(), x.double(), go.double(), rarg)
+    assert torch.allclose(gv.cpu().double(), rv, rtol=1e-4, atol=1e-4)
+    assert torch.allclose(gm.cpu().double(), rm, rtol=1e-4, atol=1e-4)

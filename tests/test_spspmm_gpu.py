@@ -102,3 +102,30 @@ def test_spspmm_reduce_errors():
             ts.matmul(src, src, red)
     with pytest.raises(RuntimeError):
         ts.matmul(src.half(), src.half())   # "sparse_matmul" not implemented for Half
+
+
+def test_c4_scale_slice_vs_oracle(oracle):
+    """BASELINE configs[3] operands (262 144 x 262 144, ~32 nnz/row): the first 16 384 rows of A times the
+    FULL B (~16.7M output nnz) against the oracle — structure bit-exact, values within 1e-5 of |A||B|;
+    plus whole-problem invariants of the full product (sorted unique columns per row, rowptr consistency)."""
+    from util import fast_random_csr
+    M = 262_144
+    _, rpa, ca = fast_random_csr(M, M, 32, 3, DEV)
+    _, rpb, cb = fast_random_csr(M, M, 32, 4, DEV)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    va = torch.randn(ca.numel(), generator=g, device=DEV)
+    vb = torch.randn(cb.numel(), generator=g, device=DEV)
+    Ms = 16_384
+    ea = int(rpa[Ms])
+    rp, r, c, v = ops.spspmm(rpa[:Ms + 1], ca[:ea], va[:ea], rpb, cb, vb, Ms, M, M, True)
+    orp, orow, oc, ov = oracle.spspmm(rpa[:Ms + 1], ca[:ea], va[:ea], rpb, cb, vb, Ms, M, M)
+    assert torch.equal(rp.cpu(), orp) and torch.equal(r.cpu(), orow) and torch.equal(c.cpu(), oc)
+    _, _, _, bound = oracle.spspmm(rpa[:Ms + 1], ca[:ea], va[:ea].abs(), rpb, cb, vb.abs(), Ms, M, M)
+    assert ((v.cpu() - ov).abs() <= 1e-5 * bound + 1e-30).all()
+    # full product: invariants only (268M nnz)
+    rp, r, c, v = ops.spspmm(rpa, ca, va, rpb, cb, vb, M, M, M, True)
+    assert int(rp[-1]) == c.numel() == r.numel() == v.numel()
+    key = r * M + c
+    assert bool((key[1:] > key[:-1]).all())                      # strictly sorted by (row, col) => unique
+    assert torch.equal(torch.bincount(r, minlength=M), rp[1:] - rp[:-1])
+    del key
