@@ -215,6 +215,9 @@ def main():
                     red[f"{name}_{op}_{dim}"] = None
     C = A.add(Bm) if hasattr(A, "add") else tsr.add(A, Bm)
     si, sv = tsr.spadd(torch.stack([ra, ca]), va, torch.stack([rb, cb]), vb, M, N)
+    dr = torch.randn(M, 1, generator=g, dtype=torch.float64)
+    dc = torch.randn(1, N, generator=g, dtype=torch.float64)
+    mr, mc = tsr.mul(A, dr), tsr.mul(A, dc)
     n0 = tsr.narrow(A, 0, 5, 20)
     n1 = tsr.narrow(A, 1, 4, 15)
     torch.save({"meta": meta,
@@ -222,6 +225,7 @@ def main():
                 "reduce": red,
                 "add": dict(row=C.storage.row(), col=C.storage.col(), value=C.storage.value()),
                 "spadd": dict(index=si, value=sv),
+                "mul": dict(dr=dr, dc=dc, row_scaled=mr.storage.value(), col_scaled=mc.storage.value()),
                 "narrow0": dict(rowptr=n0.storage.rowptr(), col=n0.storage.col(), value=n0.storage.value(), sizes=n0.sparse_sizes()),
                 "narrow1": dict(row=n1.storage.row(), col=n1.storage.col(), value=n1.storage.value(), sizes=n1.sparse_sizes())},
                GOLD / "next_rows.pt")

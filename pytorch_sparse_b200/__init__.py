@@ -14,11 +14,11 @@ from .tensor import SparseTensor  # noqa: F401
 from .matmul import matmul, spmm_sum, spmm_add, spmm_mean, spmm_min, spmm_max, spspmm_sum  # noqa: F401
 from .transpose import t, transpose  # noqa: F401
 from .functional import coalesce, spmm, spspmm  # noqa: F401
-from .add import add, spadd, narrow  # noqa: F401
+from .add import add, spadd, narrow, mul  # noqa: F401
 from .reduce import sum, mean, min, max  # noqa: F401,A004
 from . import torch_ops  # noqa: F401  (registers torch.ops.tsb200.* / torch.ops.torch_sparse.*)
 
 __version__ = "0.1.0"
 
 __all__ = ["SparseStorage", "SparseTensor", "t", "matmul", "coalesce", "transpose", "spmm", "spspmm", "spadd", "add",
-           "narrow", "sum", "mean", "min", "max", "__version__"]
+           "narrow", "mul", "sum", "mean", "min", "max", "__version__"]

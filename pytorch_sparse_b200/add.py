@@ -77,3 +77,25 @@ def narrow(src: SparseTensor, dim: int, start: int, length: int) -> SparseTensor
 
 
 SparseTensor.narrow = lambda self, dim, start, length: narrow(self, dim, start, length)
+
+
+def mul(src: SparseTensor, other: Tensor) -> SparseTensor:
+    """Scale the stored values row-wise (`other` of shape [M, 1]) or column-wise ([1, N]) — the GCN
+    normalisation step either side of SpMM (torch_sparse/mul.py:22-40, dense-operand branch). A pure
+    gather-multiply on the values; structure and caches are shared with `src`."""
+    if not isinstance(other, Tensor):
+        raise NotImplementedError("sparse * sparse is not on the sparse-matmul path")
+    row, col, value = src.coo()
+    if other.dim() >= 2 and other.size(0) == src.size(0) and other.size(1) == 1:
+        factor = other.squeeze(1)[row]
+    elif other.dim() >= 2 and other.size(0) == 1 and other.size(1) == src.size(1):
+        factor = other.squeeze(0)[col]
+    else:
+        raise ValueError(f"Size mismatch: Expected size ({src.size(0)}, 1, ...) or (1, {src.size(1)}, ...), "
+                         f"but got size {tuple(other.size())}.")
+    value = factor if value is None else factor.to(value.dtype) * value
+    return src.set_value(value, layout="coo")
+
+
+SparseTensor.mul = lambda self, other: mul(self, other)
+SparseTensor.__mul__ = lambda self, other: mul(self, other)

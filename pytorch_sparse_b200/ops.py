@@ -56,6 +56,24 @@ def _check_input(cond: bool) -> None:
         raise RuntimeError("Input mismatch")
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` costs several microseconds per call; skip it when `dev` is current."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.ctx = None if torch.cuda.current_device() == idx else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def _workspace(nbytes: int, device: torch.device) -> Optional[Tensor]:
     if nbytes <= 0:
         return None
@@ -111,7 +129,7 @@ def spmm_fw(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor,
         if arg_out is not None:
             arg_out.fill_(0)
         return out, arg_out
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nws = lib.tsb200_spmm_fw_workspace_bytes(B, M, K, E, dt, red)
         ws = _workspace(nws, dev)
         check(lib.tsb200_spmm_fw(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(arg_out),
@@ -137,7 +155,7 @@ def spmm_value_bw(row: Tensor, rowptr: Tensor, col: Tensor, mat: Tensor, grad: T
     out = torch.zeros(E, dtype=grad.dtype, device=dev)
     if E == 0 or B * K == 0:
         return out
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         check(lib.tsb200_spmm_value_bw(_p(row), _p(rowptr), _p(col), _p(mat), _p(grad), _p(out),
                                        B, M, N, K, E, _dtype_code(mat.dtype), red, _stream(dev)),
               "tsb200_spmm_value_bw")
@@ -166,7 +184,7 @@ def spmm_minmax_bw(col: Tensor, value: Optional[Tensor], mat: Tensor, grad_out: 
     gv = torch.zeros(E, dtype=acc, device=dev) if need_value else None
     gm = torch.zeros(mat.shape, dtype=acc, device=dev) if need_mat else None
     if E > 0 and B * M * K > 0 and (need_value or need_mat):
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             check(lib.tsb200_spmm_minmax_bw(_p(col), _p(value), _p(mat), _p(grad_out), _p(arg_out), _p(gv),
                                             _p(gm), B, M, N, K, E, _dtype_code(mat.dtype), _stream(dev)),
                   "tsb200_spmm_minmax_bw")
@@ -185,7 +203,7 @@ def ind2ptr(ind: Tensor, M: int) -> Tensor:
     _check_cuda(ind, "ind")
     ind = _i64(ind, "ind")
     out = torch.empty(M + 1, dtype=torch.int64, device=ind.device)
-    with torch.cuda.device(ind.device):
+    with _on_device(ind.device):
         check(lib.tsb200_ind2ptr(_p(ind), ind.numel(), M, _p(out), _stream(ind.device)), "tsb200_ind2ptr")
     return out
 
@@ -195,7 +213,7 @@ def ptr2ind(ptr: Tensor, E: int) -> Tensor:
     _check_cuda(ptr, "ptr")
     ptr = _i64(ptr, "ptr")
     out = torch.empty(E, dtype=torch.int64, device=ptr.device)
-    with torch.cuda.device(ptr.device):
+    with _on_device(ptr.device):
         check(lib.tsb200_ptr2ind(_p(ptr), ptr.numel() - 1, E, _p(out), _stream(ptr.device)), "tsb200_ptr2ind")
     return out
 
@@ -211,7 +229,7 @@ def csr2csc(row: Tensor, col: Tensor, M: int, N: int, want_colptr: bool = True,
     perm = torch.empty(E, dtype=torch.int64, device=dev)
     colptr = torch.empty(N + 1, dtype=torch.int64, device=dev) if want_colptr else None
     row_csc = torch.empty(E, dtype=torch.int64, device=dev) if want_row_csc else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nws = lib.tsb200_csr2csc_workspace_bytes(E, M, N)
         ws = _workspace(nws, dev)
         check(lib.tsb200_csr2csc(_p(row), _p(col), E, M, N, _p(perm), _p(colptr), _p(row_csc), _p(ws), nws,
@@ -234,7 +252,7 @@ def segment_reduce(ptr: Tensor, value: Tensor, reduce: str = "sum", perm: Option
         return out
     if perm is not None:
         perm = _i64(perm, "perm")
-    with torch.cuda.device(value.device):
+    with _on_device(value.device):
         check(lib.tsb200_segment_reduce(_p(ptr), _p(perm), _p(value), _p(out), S, D, _dtype_code(value.dtype),
                                         _reduce_code(reduce), _stream(value.device)), "tsb200_segment_reduce")
     return out
@@ -260,7 +278,7 @@ def sort_perm(row: Tensor, col: Tensor, M: int, N: int) -> Optional[Tensor]:
     E, dev = col.numel(), col.device
     if E < 2:
         return None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nws = lib.tsb200_coalesce_workspace_bytes(E, M, N)
         ws = _workspace(nws, dev)
         st = _stream(dev)
@@ -287,7 +305,7 @@ def coalesce(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int,
         value = value.contiguous()
     if E == 0:
         return row, col, value
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nws = lib.tsb200_coalesce_workspace_bytes(E, M, N)
         ws = _workspace(nws, dev)
         st = _stream(dev)
@@ -333,7 +351,7 @@ def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: T
         val_a = val_b = None
     nnz_a, nnz_b = col_a.numel(), col_b.numel()
     rowptr_c = torch.empty(M + 1, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         nws = lib.tsb200_spspmm_workspace_bytes(M, Kd, N, nnz_a, nnz_b)
         ws = _workspace(nws, dev)
         st = _stream(dev)

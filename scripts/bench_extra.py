@@ -36,6 +36,29 @@ if "pcie" in which:
     ms_dn = timeit(lambda: h.copy_(d, non_blocking=True), 5, 1)
     out(what="pcie_pinned_256MB", h2d_gbs=256 / 1024 / ms_up * 1e3, d2h_gbs=256 / 1024 / ms_dn * 1e3)
 
+if "overhead" in which:  # host-side launch cost of one small SpMM through the public API (no sync inside the loop)
+    M = 10_000
+    row, rowptr, col = fast_random_csr(M, M, 5, 1, dev)
+    a = ts.SparseTensor(row=row, rowptr=rowptr, col=col, value=torch.rand(col.numel(), device=dev), sparse_sizes=(M, M),
+                        is_sorted=True, trust_data=True)
+    x = torch.randn(M, 32, device=dev)
+    for _ in range(50):
+        a @ x
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        a @ x
+    host_us = (time.perf_counter() - t0) / 2000 * 1e6
+    torch.cuda.synchronize()
+    t_dev = timeit(lambda: a @ x, 200, 10) * 1e3
+    rowptr_, col_, val_ = a.csr()
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        ops.spmm_fw(rowptr_, col_, val_, x, "sum")
+    torch.cuda.synchronize()
+    raw_us = (time.perf_counter() - t0) / 2000 * 1e6
+    out(what="c1_overhead", api_host_us_per_call=host_us, device_us_per_call=t_dev, ops_spmm_fw_us_per_call=raw_us)
+
 if "e2e" in which:
     M = 1_000_000; F = 128
     row, rowptr, col = fast_random_csr(M, M, 16, 1, dev)

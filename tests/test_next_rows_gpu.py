@@ -80,3 +80,23 @@ def test_segment_reduce_vs_oracle(oracle, dtype, reduce):
     out_p = ops.segment_reduce(rowptr.to(DEV), v.to(DEV), reduce, perm=perm.to(DEV))
     ref_p = oracle.segment_reduce(rowptr, v, reduce, perm=perm)
     assert torch.allclose(out_p.cpu().double(), ref_p.double(), rtol=1e-5, atol=1e-3)
+
+
+def test_mul_vs_reference_and_gcn_flow():
+    """row / column scaling (torch_sparse/mul.py:22-40) vs golden, then the GCN normalisation flow
+    D^-1/2 (A) D^-1/2 X built from sum(dim) + mul + matmul against a dense computation."""
+    i = D["in"]
+    a = _mk("v")
+    mr = ts.mul(a, D["mul"]["dr"].to(DEV))
+    mc = a * D["mul"]["dc"].to(DEV)
+    assert torch.equal(mr.storage.value().cpu(), D["mul"]["row_scaled"])
+    assert torch.equal(mc.storage.value().cpu(), D["mul"]["col_scaled"])
+    adj = ts.SparseTensor(row=i["ra"].to(DEV), col=i["ca"].to(DEV), value=i["va"].abs().to(DEV) + 0.1,
+                          sparse_sizes=(i["M"], i["N"]))
+    deg_r = adj.sum(dim=1).clamp(min=1e-12)
+    deg_c = adj.sum(dim=0).clamp(min=1e-12)
+    norm = adj.mul(deg_r.pow(-0.5).view(-1, 1)).mul(deg_c.pow(-0.5).view(1, -1))
+    x = torch.randn(i["N"], 16, device=DEV, dtype=torch.float64)
+    dense = adj.to_dense()
+    ref = (deg_r.pow(-0.5).view(-1, 1) * dense * deg_c.pow(-0.5).view(1, -1)) @ x
+    assert torch.allclose(norm @ x, ref, atol=1e-10)
