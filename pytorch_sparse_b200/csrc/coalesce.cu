@@ -18,15 +18,18 @@
 
 namespace tsb {
 
+// ib > 0: "packed" mode — the input position i is stored in the low ib bits of the key word, so the radix
+// sort moves 8-byte keys only (no payload); it sorts bits [ib, ib+key_bits) and, being stable, leaves equal
+// keys in input order. ib == 0: separate 32-bit payload array (keys wider than 64 - bits(E)).
 __global__ void coalesce_keys_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col,
                                      int64_t E, int64_t N, uint64_t* __restrict__ keys,
-                                     uint32_t* __restrict__ perm, int* __restrict__ unsorted) {
+                                     uint32_t* __restrict__ perm, int* __restrict__ unsorted, int ib) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   bool bad = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride) {
     const uint64_t k = (uint64_t)(row[i] * N + col[i]);
-    keys[i] = k;
-    perm[i] = (uint32_t)i;
+    if (ib) keys[i] = (k << ib) | (uint64_t)i;
+    else { keys[i] = k; perm[i] = (uint32_t)i; }
     if (i > 0) {
       const uint64_t kp = (uint64_t)(__ldg(row + i - 1) * N + __ldg(col + i - 1));
       bad |= k < kp;
@@ -35,17 +38,20 @@ __global__ void coalesce_keys_kernel(const int64_t* __restrict__ row, const int6
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(unsorted, 1);
 }
 
-__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t E, uint8_t* __restrict__ flags) {
+__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t E, uint8_t* __restrict__ flags, int ib) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride)
-    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+    flags[i] = (i == 0 || (keys[i] >> ib) != (keys[i - 1] >> ib)) ? 1 : 0;
 }
 
 __global__ void copy_count_kernel(const int* __restrict__ n_sel, int64_t* __restrict__ out) { *out = (int64_t)*n_sel; }
 
-__global__ void widen_perm_kernel(const uint32_t* __restrict__ perm, int64_t E, int64_t* __restrict__ out) {
+__global__ void widen_perm_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm, int64_t E,
+                                  int64_t* __restrict__ out, int ib) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride) out[i] = (int64_t)perm[i];
+  const uint64_t mask = ib ? (((uint64_t)1 << ib) - 1) : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride)
+    out[i] = ib ? (int64_t)(keys[i] & mask) : (int64_t)perm[i];
 }
 
 enum { C_SUM = TSB200_SUM, C_MEAN = TSB200_MEAN, C_MIN = TSB200_MIN, C_MAX = TSB200_MAX };
@@ -55,8 +61,10 @@ __global__ void __launch_bounds__(256)
 coalesce_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
                      const uint32_t* __restrict__ starts, int64_t E, int64_t N, int64_t n_unique,
                      const T* __restrict__ value_in, int64_t D, int reduce, int64_t* __restrict__ row_out,
-                     int64_t* __restrict__ col_out, T* __restrict__ value_out, int64_t* __restrict__ perm_out) {
+                     int64_t* __restrict__ col_out, T* __restrict__ value_out, int64_t* __restrict__ perm_out, int ib) {
   using acc_t = typename Traits<T>::acc_t;
+  const uint64_t pmask = ib ? (((uint64_t)1 << ib) - 1) : 0;
+  auto perm_at = [&](int64_t j) -> int64_t { return ib ? (int64_t)(keys[j] & pmask) : (int64_t)perm[j]; };
   const int64_t total = n_unique * (value_in ? D : 1);
   const int64_t Dd = value_in ? D : 1;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -65,16 +73,16 @@ coalesce_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
     const int64_t s = starts[seg];
     const int64_t e = (seg + 1 < n_unique) ? (int64_t)starts[seg + 1] : E;
     if (d == 0) {
-      const uint64_t k = keys[s];
+      const uint64_t k = keys[s] >> ib;
       const uint64_t r = k / (uint64_t)N;
       if (row_out) row_out[seg] = (int64_t)r;
       if (col_out) col_out[seg] = (int64_t)(k - r * (uint64_t)N);
-      if (perm_out) perm_out[seg] = (int64_t)perm[s];
+      if (perm_out) perm_out[seg] = perm_at(s);
     }
     if (value_in) {
-      acc_t a = Traits<T>::to_acc(value_in[(int64_t)perm[s] * D + d]);
+      acc_t a = Traits<T>::to_acc(value_in[perm_at(s) * D + d]);
       for (int64_t j = s + 1; j < e; j++) {
-        const acc_t v = Traits<T>::to_acc(value_in[(int64_t)perm[j] * D + d]);
+        const acc_t v = Traits<T>::to_acc(value_in[perm_at(j) * D + d]);
         if (reduce == C_SUM || reduce == C_MEAN) a = a + v;
         else if (reduce == C_MIN) a = v < a ? v : a;
         else a = v > a ? v : a;
@@ -88,7 +96,7 @@ coalesce_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
 struct CoLayout {
   size_t k0, k1, p0, p1, flags, starts, scalars, cub, total;
   size_t cub_bytes;
-  // scalars: [0] int unsorted, [1] int n_selected, [2..3] int64 n_unique, [4] int keys_cur, [5] int perm_cur
+  // scalars: [0] int unsorted, [1] int n_selected, [2..3] int64 n_unique, [4] int keys_cur, [5] int perm_cur, [6] int ib
 };
 static CoLayout co_layout(int64_t E) {
   CoLayout L;
@@ -105,6 +113,11 @@ static CoLayout co_layout(int64_t E) {
   cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
   cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
   cub::DeviceRadixSort::SortPairs(nullptr, t1, dk, dv, (int)n, 0, 64, (cudaStream_t)0);
+  {
+    size_t t3 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, t3, dk, (int)n, 0, 64, (cudaStream_t)0);
+    if (t3 > t1) t1 = t3;
+  }
   cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr,
                              (uint32_t*)nullptr, (int*)nullptr, (int)n, (cudaStream_t)0);
   L.cub_bytes = t1 > t2 ? t1 : t2;
@@ -152,29 +165,39 @@ extern "C" int tsb200_coalesce_sort(const int64_t* row, const int64_t* col, int6
   if (!row || !col) return TSB200_ERR_INVALID_ARG;
   uint64_t* k0 = (uint64_t*)(ws + L.k0); uint64_t* k1 = (uint64_t*)(ws + L.k1);
   uint32_t* p0 = (uint32_t*)(ws + L.p0); uint32_t* p1 = (uint32_t*)(ws + L.p1);
-  coalesce_keys_kernel<<<cgrid(E), 256, 0, st>>>(row, col, E, N, k0, p0, sc);
+  // key width and packing decision
+  int bits = 1;
+  {
+    const unsigned __int128 maxkey = (unsigned __int128)(M > 0 ? M : 1) * (unsigned __int128)(N > 0 ? N : 1);
+    while (bits < 64 && ((unsigned __int128)1 << bits) < maxkey) bits++;
+  }
+  int ebits = 1;
+  while (((int64_t)1 << ebits) < E) ebits++;
+  const int ib = (bits + ebits <= 64) ? ebits : 0;
+  coalesce_keys_kernel<<<cgrid(E), 256, 0, st>>>(row, col, E, N, k0, p0, sc, ib);
   TSB_LAUNCH_CHECK();
   int unsorted = 0;
   TSB_CUDA_TRY(cudaMemcpyAsync(&unsorted, sc, sizeof(int), cudaMemcpyDeviceToHost, st));
   TSB_CUDA_TRY(cudaStreamSynchronize(st));
   int cur = 0;
   if (unsorted) {
-    // significant bits of the largest possible key M*N-1
-    int bits = 1;
-    const unsigned __int128 maxkey = (unsigned __int128)(M > 0 ? M : 1) * (unsigned __int128)(N > 0 ? N : 1);
-    while (bits < 64 && ((unsigned __int128)1 << bits) < maxkey) bits++;
-    cub::DoubleBuffer<uint64_t> dk(k0, k1);
-    cub::DoubleBuffer<uint32_t> dv(p0, p1);
     size_t tb = L.cub_bytes;
-    TSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, dk, dv, (int)E, 0, bits, st));
-    cur = (dk.Current() == k1) ? 1 : 0;
-    // CUB keeps keys and values in the same selector
+    if (ib) {
+      cub::DoubleBuffer<uint64_t> dk(k0, k1);
+      TSB_CUDA_TRY(cub::DeviceRadixSort::SortKeys(ws + L.cub, tb, dk, (int)E, ib, ib + bits, st));
+      cur = (dk.Current() == k1) ? 1 : 0;
+    } else {
+      cub::DoubleBuffer<uint64_t> dk(k0, k1);
+      cub::DoubleBuffer<uint32_t> dv(p0, p1);
+      TSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ws + L.cub, tb, dk, dv, (int)E, 0, bits, st));
+      cur = (dk.Current() == k1) ? 1 : 0;  // CUB keeps keys and values in the same selector
+    }
   }
-  int h[2] = {cur, cur};
+  int h[3] = {cur, cur, ib};
   TSB_CUDA_TRY(cudaMemcpyAsync(sc + 4, h, sizeof(h), cudaMemcpyHostToDevice, st));
   const uint64_t* keys = cur ? k1 : k0;
   uint8_t* flags = (uint8_t*)(ws + L.flags);
-  head_flags_kernel<<<cgrid(E), 256, 0, st>>>(keys, E, flags);
+  head_flags_kernel<<<cgrid(E), 256, 0, st>>>(keys, E, flags, ib);
   TSB_LAUNCH_CHECK();
   size_t tb = L.cub_bytes;
   TSB_CUDA_TRY(cub::DeviceSelect::Flagged(ws + L.cub, tb, cub::CountingInputIterator<uint32_t>(0), flags,
@@ -200,24 +223,25 @@ extern "C" int tsb200_coalesce_emit(int64_t E, int64_t N, int64_t n_unique, cons
   // which half of the double buffers holds the sorted data: recorded by phase 1 on the device;
   // phase 1 already synchronised once and the caller synchronised to read E', so a tiny D2H here
   // is a read of settled data.
-  int h[2] = {0, 0};
+  int h[3] = {0, 0, 0};
   TSB_CUDA_TRY(cudaMemcpyAsync(h, ws + L.scalars + 16, sizeof(h), cudaMemcpyDeviceToHost, st));
   TSB_CUDA_TRY(cudaStreamSynchronize(st));
   const uint64_t* keys = (const uint64_t*)(ws + (h[0] ? L.k1 : L.k0));
   const uint32_t* perm = (const uint32_t*)(ws + (h[1] ? L.p1 : L.p0));
   const uint32_t* starts = (const uint32_t*)(ws + L.starts);
+  const int ib = h[2];
   if (value_in && D == 0) value_in = nullptr;
   const int64_t total = n_unique * (value_in ? D : 1);
   if (!value_in) {
     coalesce_emit_kernel<float><<<cgrid(total), 256, 0, st>>>(keys, perm, starts, E, N, n_unique, nullptr, 1, reduce,
-                                                             row_out, col_out, nullptr, perm_out);
+                                                             row_out, col_out, nullptr, perm_out, ib);
     TSB_LAUNCH_CHECK();
     return 0;
   }
   return dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     coalesce_emit_kernel<T><<<cgrid(total), 256, 0, st>>>(keys, perm, starts, E, N, n_unique, (const T*)value_in, D,
-                                                         reduce, row_out, col_out, (T*)value_out, perm_out);
+                                                         reduce, row_out, col_out, (T*)value_out, perm_out, ib);
     TSB_LAUNCH_CHECK();
     return 0;
   });
@@ -231,11 +255,12 @@ extern "C" int tsb200_coalesce_perm(int64_t E, int64_t* perm_out, const void* wo
   cudaStream_t st = (cudaStream_t)stream;
   const CoLayout L = co_layout(E);
   const char* ws = (const char*)workspace;
-  int h[2] = {0, 0};
+  int h[3] = {0, 0, 0};
   TSB_CUDA_TRY(cudaMemcpyAsync(h, ws + L.scalars + 16, sizeof(h), cudaMemcpyDeviceToHost, st));
   TSB_CUDA_TRY(cudaStreamSynchronize(st));
+  const uint64_t* keys = (const uint64_t*)(ws + (h[0] ? L.k1 : L.k0));
   const uint32_t* perm = (const uint32_t*)(ws + (h[1] ? L.p1 : L.p0));
-  widen_perm_kernel<<<cgrid(E), 256, 0, st>>>(perm, E, perm_out);
+  widen_perm_kernel<<<cgrid(E), 256, 0, st>>>(keys, perm, E, perm_out, h[2]);
   TSB_LAUNCH_CHECK();
   return 0;
 }
