@@ -2,9 +2,11 @@
 // the HOST-buffer SpMM call (the end-to-end path a reference-side binding takes when it holds CPU
 // tensors, cf. spmm_cpu(rowptr, col, value, mat, reduce), csrc/cpu/spmm_cpu.cpp:8-11).
 //
-// tsb200_spmm_fw_host pipelines PCIe against the kernel: `mat` goes up first, then the CSR arrays
-// in row chunks; each chunk's SpMM starts as soon as its indices have landed and its output rows
-// are copied back on a second stream while later chunks are still uploading (PCIe is full duplex).
+// tsb200_spmm_fw_host pipelines PCIe against the kernel: `mat` goes up first, split over TWO upload
+// streams (one DMA stream tops out at ~40 GB/s H2D on these hosts, two reach ~51 GB/s), then the CSR
+// arrays in row chunks alternating between the two; each chunk's SpMM starts on a compute stream as soon
+// as its indices have landed and its output rows are copied back on a fourth stream while later chunks
+// are still uploading (the link sustains ~87 GB/s bidirectional).
 #include <cstdlib>
 #include <mutex>
 
@@ -17,9 +19,9 @@ struct HostCtx {
   int device = -1;
   char* buf = nullptr;
   size_t cap = 0;
-  cudaStream_t s_up = nullptr, s_down = nullptr;
+  cudaStream_t s_up[2] = {nullptr, nullptr}, s_comp = nullptr, s_down = nullptr;
   static constexpr int kMaxChunks = 16;
-  cudaEvent_t ev_chunk[kMaxChunks] = {};
+  cudaEvent_t ev_up[kMaxChunks] = {}, ev_comp[kMaxChunks] = {}, ev_mat[2] = {}, ev_rowptr = nullptr;
   bool init = false;
 };
 static HostCtx g_host;
@@ -69,10 +71,17 @@ extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* co
   int dev = 0;
   TSB_CUDA_TRY(cudaGetDevice(&dev));
   if (!c.init || c.device != dev) {
-    TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_up, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_up[i], cudaStreamNonBlocking));
+      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_mat[i], cudaEventDisableTiming));
+    }
+    TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_comp, cudaStreamNonBlocking));
     TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_down, cudaStreamNonBlocking));
-    for (int i = 0; i < HostCtx::kMaxChunks; i++)
-      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_chunk[i], cudaEventDisableTiming));
+    TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_rowptr, cudaEventDisableTiming));
+    for (int i = 0; i < HostCtx::kMaxChunks; i++) {
+      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_up[i], cudaEventDisableTiming));
+      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_comp[i], cudaEventDisableTiming));
+    }
     c.buf = nullptr; c.cap = 0; c.device = dev; c.init = true;
   }
   // device layout
@@ -96,8 +105,20 @@ extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* co
   int64_t* d_col = (int64_t*)(d + o_col);
   void* d_val = value_host ? (void*)(d + o_val) : nullptr;
 
-  TSB_CUDA_TRY(cudaMemcpyAsync(d + o_mat, mat_host, (size_t)B * N * K * es, cudaMemcpyHostToDevice, c.s_up));
-  TSB_CUDA_TRY(cudaMemcpyAsync(d_rowptr, rowptr_host, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, c.s_up));
+  // dense operand: two halves on the two upload streams; rowptr rides on stream 0
+  {
+    const size_t mat_bytes = (size_t)B * N * K * es;
+    const size_t half = align_up(mat_bytes / 2, 4096) < mat_bytes ? align_up(mat_bytes / 2, 4096) : mat_bytes;
+    TSB_CUDA_TRY(cudaMemcpyAsync(d + o_mat, mat_host, half, cudaMemcpyHostToDevice, c.s_up[0]));
+    if (mat_bytes > half)
+      TSB_CUDA_TRY(cudaMemcpyAsync(d + o_mat + half, (const char*)mat_host + half, mat_bytes - half,
+                                   cudaMemcpyHostToDevice, c.s_up[1]));
+    TSB_CUDA_TRY(cudaMemcpyAsync(d_rowptr, rowptr_host, (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, c.s_up[0]));
+    TSB_CUDA_TRY(cudaEventRecord(c.ev_mat[0], c.s_up[0]));
+    TSB_CUDA_TRY(cudaEventRecord(c.ev_mat[1], c.s_up[1]));
+    TSB_CUDA_TRY(cudaStreamWaitEvent(c.s_comp, c.ev_mat[0], 0));
+    TSB_CUDA_TRY(cudaStreamWaitEvent(c.s_comp, c.ev_mat[1], 0));
+  }
 
   // chunking only pays (and only keeps out/arg_out contiguous per copy) for a single batch
   int nchunk = (B == 1 && M >= 4096 && E >= (1 << 20)) ? 8 : 1;
@@ -106,22 +127,25 @@ extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* co
     if (v >= 1 && v <= HostCtx::kMaxChunks && B == 1) nchunk = v;
   }
   for (int ch = 0; ch < nchunk; ch++) {
+    cudaStream_t up = c.s_up[ch & 1];
     const int64_t r0 = M * ch / nchunk, r1 = M * (ch + 1) / nchunk;
     const int64_t e0 = rowptr_host[r0], e1 = rowptr_host[r1];
     if (e1 > e0) {
-      TSB_CUDA_TRY(cudaMemcpyAsync(d_col + e0, col_host + e0, (size_t)(e1 - e0) * 8, cudaMemcpyHostToDevice, c.s_up));
+      TSB_CUDA_TRY(cudaMemcpyAsync(d_col + e0, col_host + e0, (size_t)(e1 - e0) * 8, cudaMemcpyHostToDevice, up));
       if (value_host)
         TSB_CUDA_TRY(cudaMemcpyAsync((char*)d_val + e0 * es, (const char*)value_host + e0 * es,
-                                     (size_t)(e1 - e0) * es, cudaMemcpyHostToDevice, c.s_up));
+                                     (size_t)(e1 - e0) * es, cudaMemcpyHostToDevice, up));
     }
+    TSB_CUDA_TRY(cudaEventRecord(c.ev_up[ch], up));
+    TSB_CUDA_TRY(cudaStreamWaitEvent(c.s_comp, c.ev_up[ch], 0));
     if (r1 > r0) {
       int rc = tsb200_spmm_fw(d_rowptr + r0, d_col, d_val, d + o_mat, d + o_out + (size_t)r0 * K * es,
                               arg ? (int64_t*)(d + o_arg) + r0 * K : nullptr, B, r1 - r0, N, K, E, dtype, reduce,
-                              ws_bytes ? d + o_ws : nullptr, ws_bytes, c.s_up);
+                              ws_bytes ? d + o_ws : nullptr, ws_bytes, c.s_comp);
       if (rc) return rc;
     }
-    TSB_CUDA_TRY(cudaEventRecord(c.ev_chunk[ch], c.s_up));
-    TSB_CUDA_TRY(cudaStreamWaitEvent(c.s_down, c.ev_chunk[ch], 0));
+    TSB_CUDA_TRY(cudaEventRecord(c.ev_comp[ch], c.s_comp));
+    TSB_CUDA_TRY(cudaStreamWaitEvent(c.s_down, c.ev_comp[ch], 0));
     if (r1 > r0) {
       const size_t rows = (size_t)(nchunk == 1 ? B * M : (r1 - r0));
       TSB_CUDA_TRY(cudaMemcpyAsync((char*)out_host + (size_t)r0 * K * es, d + o_out + (size_t)r0 * K * es,
@@ -131,7 +155,9 @@ extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* co
                                      cudaMemcpyDeviceToHost, c.s_down));
     }
   }
-  TSB_CUDA_TRY(cudaStreamSynchronize(c.s_up));
+  TSB_CUDA_TRY(cudaStreamSynchronize(c.s_up[0]));
+  TSB_CUDA_TRY(cudaStreamSynchronize(c.s_up[1]));
+  TSB_CUDA_TRY(cudaStreamSynchronize(c.s_comp));
   TSB_CUDA_TRY(cudaStreamSynchronize(c.s_down));
   return 0;
 }

@@ -372,9 +372,38 @@ def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: T
     return rowptr_c, row_c, col_c, val_c
 
 
-def spmm_fw_host(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor,
-                 reduce: str = "sum") -> Tuple[Tensor, Optional[Tensor]]:
-    """Host-buffer SpMM: CPU tensors in, CPU tensors out, H2D/D2H inside (tsb200_spmm_fw_host)."""
+_PINNED_POOL: dict = {}   # nbytes -> list of (pinned uint8 tensor, idle use-count); cudaHostAlloc of 256 MB costs ~30 ms
+
+
+def _storage_uses(t: Tensor) -> int:
+    return torch._C._storage_Use_Count(t.untyped_storage()._cdata)
+
+
+def _pinned_empty(shape, dtype: torch.dtype, pin: bool = True) -> Tensor:
+    """A pinned host tensor from a small pool. A pooled buffer is handed out again only when no tensor other
+    than the pool's own handle references its storage any more (every view a caller derived from an earlier
+    result holds a storage reference, so the C++ use-count tells)."""
+    esize = torch.empty(0, dtype=dtype).element_size()
+    numel = int(torch.Size(shape).numel())
+    nbytes = max(1, numel * esize)
+    bucket = _PINNED_POOL.setdefault((nbytes, pin), [])
+    base = None
+    for cand, idle in bucket:
+        if _storage_uses(cand) <= idle:
+            base = cand
+            break
+    if base is None:
+        base = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
+        if len(bucket) < 4:
+            bucket.append((base, _storage_uses(base)))
+    return base[:numel * esize].view(dtype).view(shape)
+
+
+def spmm_fw_host(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor, reduce: str = "sum",
+                 out: Optional[Tensor] = None, arg_out: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """Host-buffer SpMM: CPU tensors in, CPU tensors out, H2D/D2H inside (tsb200_spmm_fw_host). Pass pinned
+    tensors for full PCIe speed; `out` / `arg_out` may be supplied (pinned, right shape/dtype), otherwise
+    they come from a pinned pool when `mat` is pinned."""
     for t, n in ((rowptr, "rowptr"), (col, "col"), (mat, "mat")):
         if t.is_cuda:
             raise RuntimeError(f"{n} must be CPU tensor")
@@ -387,9 +416,18 @@ def spmm_fw_host(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tens
     B = mat.numel() // (N * K) if N * K > 0 else 0
     sizes = list(mat.shape)
     sizes[-2] = M
-    pin = mat.is_pinned()
-    out = torch.empty(sizes, dtype=mat.dtype, pin_memory=pin)
-    arg_out = torch.empty(sizes, dtype=torch.int64, pin_memory=pin) if red >= 2 else None
+    alloc = _pinned_empty if mat.is_pinned() else (lambda shape, dtype: torch.empty(shape, dtype=dtype))
+    if out is None:
+        out = alloc(sizes, mat.dtype)
+    else:
+        _check_input(list(out.shape) == sizes and out.dtype == mat.dtype and out.is_contiguous() and not out.is_cuda)
+    if red >= 2:
+        if arg_out is None:
+            arg_out = alloc(sizes, torch.int64)
+        else:
+            _check_input(list(arg_out.shape) == sizes and arg_out.dtype == torch.int64 and arg_out.is_contiguous())
+    else:
+        arg_out = None
     check(lib.tsb200_spmm_fw_host(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(arg_out), B, M, N, K,
                                   col.numel(), _dtype_code(mat.dtype), red), "tsb200_spmm_fw_host")
     return out, arg_out

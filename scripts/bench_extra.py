@@ -35,6 +35,32 @@ if "pcie" in which:
     ms_up = timeit(lambda: d.copy_(h, non_blocking=True), 5, 1)
     ms_dn = timeit(lambda: h.copy_(d, non_blocking=True), 5, 1)
     out(what="pcie_pinned_256MB", h2d_gbs=256 / 1024 / ms_up * 1e3, d2h_gbs=256 / 1024 / ms_dn * 1e3)
+    for ns in (2, 4, 8):
+        streams = [torch.cuda.Stream() for _ in range(ns)]
+        chunk = (256 << 20) // ns
+        def multi():
+            ev = torch.cuda.Event(); ev.record()
+            for i, st in enumerate(streams):
+                st.wait_event(ev)
+                with torch.cuda.stream(st):
+                    d[i * chunk:(i + 1) * chunk].copy_(h[i * chunk:(i + 1) * chunk], non_blocking=True)
+            for st in streams:
+                torch.cuda.current_stream().wait_stream(st)
+        ms = timeit(multi, 5, 1)
+        out(what=f"pcie_h2d_{ns}_streams", gbs=256 / 1024 / ms * 1e3)
+    # simultaneous H2D + D2H
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    h2 = torch.empty(256 << 20, dtype=torch.uint8).pin_memory(); d2 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    def both():
+        ev = torch.cuda.Event(); ev.record()
+        s1.wait_event(ev); s2.wait_event(ev)
+        with torch.cuda.stream(s1):
+            d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h2.copy_(d2, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1); torch.cuda.current_stream().wait_stream(s2)
+    ms = timeit(both, 5, 1)
+    out(what="pcie_bidirectional_256MB_each", ms=ms, agg_gbs=512 / 1024 / ms * 1e3)
 
 if "overhead" in which:  # host-side launch cost of one small SpMM through the public API (no sync inside the loop)
     M = 10_000
@@ -73,6 +99,23 @@ if "e2e" in which:
     ms = (time.perf_counter() - t0) * 1e3 / 5
     import os
     out(what="e2e_host_c2", chunks=os.environ.get("TSB200_HOST_CHUNKS", "default"), ms=ms)
+    # split: pinned allocation vs the library call with a preallocated pinned output
+    t0 = time.perf_counter()
+    for _ in range(5):
+        tmp = torch.empty(M, F, dtype=torch.bfloat16, pin_memory=True)
+    alloc_ms = (time.perf_counter() - t0) * 1e3 / 5
+    import ctypes
+    from pytorch_sparse_b200._lib import lib
+    o = torch.empty(M, F, dtype=torch.bfloat16, pin_memory=True)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    def raw():
+        return lib.tsb200_spmm_fw_host(P(rp_h), P(col_h), P(val_h), P(x_h), P(o), None, 1, M, M, F, col_h.numel(), 3, 0)
+    raw(); raw()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        rc = raw()
+    raw_ms = (time.perf_counter() - t0) * 1e3 / 5
+    out(what="e2e_split", pinned_alloc_256MB_ms=alloc_ms, lib_call_ms=raw_ms, rc=rc)
 
 if "c2bw" in which:  # SpMM_sum fwd+bwd at C2 (value grad + dense grad)
     M = 1_000_000; F = 128

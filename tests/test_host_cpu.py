@@ -187,3 +187,18 @@ def test_row_sharded_spmm_gloo_world2(oracle, tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_pinned_output_pool_never_aliases_live_results():
+    """spmm_fw_host's output pool: a buffer is reused only after every tensor derived from an earlier
+    result is gone (pin=False here: same logic, no CUDA needed)."""
+    a = ops._pinned_empty((4, 8), torch.bfloat16, pin=False)
+    b = ops._pinned_empty((4, 8), torch.bfloat16, pin=False)
+    assert a.data_ptr() != b.data_ptr()
+    pa, view = a.data_ptr(), a[:2]
+    del a
+    c = ops._pinned_empty((4, 8), torch.bfloat16, pin=False)
+    assert c.data_ptr() != pa          # a derived view is still alive
+    del view
+    d = ops._pinned_empty((4, 8), torch.bfloat16, pin=False)
+    assert d.data_ptr() == pa          # now it may be reused
