@@ -248,6 +248,8 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
   float acc[NA];
   int arg[ARG ? NA : 1];
 
+  __device__ __forceinline__ float acc_float(int i) const { return acc[i]; }
+
   __device__ __forceinline__ void init() {
 #pragma unroll
     for (int i = 0; i < NA; i++) {
@@ -395,10 +397,181 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
   }
 };
 
+// ---- packed 16-bit min/max engine --------------------------------------------------------------
+// For bf16 / f16 the reference compares products ROUNDED to the storage type, so the whole min/max
+// recurrence can stay in packed 16-bit pairs: HMUL2 (round-to-nearest product of two pairs), HSETP2
+// (two strict compares -> two predicates, false on NaN like the reference's `>`), HMNMX2 (new extreme) —
+// ~20 instructions per gathered 16-byte vector instead of ~57 for unpack / fp32 multiply / re-round /
+// compare / select. Values are bit-identical to the float path; ties still keep the smallest nnz index.
+template <typename T> struct Pk;
+template <> struct Pk<__nv_bfloat16> {
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) {
+    uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+  }
+  template <bool MAX> static __device__ __forceinline__ void step(uint32_t& acc, int& a0, int& a1, uint32_t p, int j) {
+    if (MAX) asm("{\n\t.reg .pred q0, q1;\n\tsetp.gt.bf16x2 q0|q1, %3, %2;\n\t@q0 mov.b32 %0, %4;\n\t@q1 mov.b32 %1, %4;\n\t"
+                 "max.bf16x2 %2, %2, %3;\n\t}" : "+r"(a0), "+r"(a1), "+r"(acc) : "r"(p), "r"(j));
+    else asm("{\n\t.reg .pred q0, q1;\n\tsetp.lt.bf16x2 q0|q1, %3, %2;\n\t@q0 mov.b32 %0, %4;\n\t@q1 mov.b32 %1, %4;\n\t"
+             "min.bf16x2 %2, %2, %3;\n\t}" : "+r"(a0), "+r"(a1), "+r"(acc) : "r"(p), "r"(j));
+  }
+  // per-half masks: better (strict) and equal
+  template <bool MAX> static __device__ __forceinline__ void cmp(uint32_t o, uint32_t m, bool& b0, bool& b1, bool& e0, bool& e1) {
+    uint32_t x0, x1, y0, y1;
+    if (MAX) asm("{\n\t.reg .pred q0, q1;\n\tsetp.gt.bf16x2 q0|q1, %4, %5;\n\tselp.u32 %0, 1, 0, q0;\n\tselp.u32 %1, 1, 0, q1;\n\t"
+                 "setp.eq.bf16x2 q0|q1, %4, %5;\n\tselp.u32 %2, 1, 0, q0;\n\tselp.u32 %3, 1, 0, q1;\n\t}"
+                 : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(o), "r"(m));
+    else asm("{\n\t.reg .pred q0, q1;\n\tsetp.lt.bf16x2 q0|q1, %4, %5;\n\tselp.u32 %0, 1, 0, q0;\n\tselp.u32 %1, 1, 0, q1;\n\t"
+             "setp.eq.bf16x2 q0|q1, %4, %5;\n\tselp.u32 %2, 1, 0, q0;\n\tselp.u32 %3, 1, 0, q1;\n\t}"
+             : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(o), "r"(m));
+    b0 = x0; b1 = x1; e0 = y0; e1 = y1;
+  }
+  static __device__ __forceinline__ uint32_t splat(unsigned short v) { return (uint32_t)v | ((uint32_t)v << 16); }
+  static __device__ __forceinline__ float half_to_float(uint32_t w, int hi) {
+    return __uint_as_float(hi ? (w & 0xffff0000u) : (w << 16));
+  }
+  static __device__ __forceinline__ uint32_t extreme(bool max_) { return max_ ? 0xFF7FFF7Fu : 0x7F7F7F7Fu; }  // lowest / highest
+};
+template <> struct Pk<__half> {
+  static __device__ __forceinline__ uint32_t mul(uint32_t a, uint32_t b) {
+    uint32_t r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+  }
+  template <bool MAX> static __device__ __forceinline__ void step(uint32_t& acc, int& a0, int& a1, uint32_t p, int j) {
+    if (MAX) asm("{\n\t.reg .pred q0, q1;\n\tsetp.gt.f16x2 q0|q1, %3, %2;\n\t@q0 mov.b32 %0, %4;\n\t@q1 mov.b32 %1, %4;\n\t"
+                 "max.f16x2 %2, %2, %3;\n\t}" : "+r"(a0), "+r"(a1), "+r"(acc) : "r"(p), "r"(j));
+    else asm("{\n\t.reg .pred q0, q1;\n\tsetp.lt.f16x2 q0|q1, %3, %2;\n\t@q0 mov.b32 %0, %4;\n\t@q1 mov.b32 %1, %4;\n\t"
+             "min.f16x2 %2, %2, %3;\n\t}" : "+r"(a0), "+r"(a1), "+r"(acc) : "r"(p), "r"(j));
+  }
+  template <bool MAX> static __device__ __forceinline__ void cmp(uint32_t o, uint32_t m, bool& b0, bool& b1, bool& e0, bool& e1) {
+    uint32_t x0, x1, y0, y1;
+    if (MAX) asm("{\n\t.reg .pred q0, q1;\n\tsetp.gt.f16x2 q0|q1, %4, %5;\n\tselp.u32 %0, 1, 0, q0;\n\tselp.u32 %1, 1, 0, q1;\n\t"
+                 "setp.eq.f16x2 q0|q1, %4, %5;\n\tselp.u32 %2, 1, 0, q0;\n\tselp.u32 %3, 1, 0, q1;\n\t}"
+                 : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(o), "r"(m));
+    else asm("{\n\t.reg .pred q0, q1;\n\tsetp.lt.f16x2 q0|q1, %4, %5;\n\tselp.u32 %0, 1, 0, q0;\n\tselp.u32 %1, 1, 0, q1;\n\t"
+             "setp.eq.f16x2 q0|q1, %4, %5;\n\tselp.u32 %2, 1, 0, q0;\n\tselp.u32 %3, 1, 0, q1;\n\t}"
+             : "=r"(x0), "=r"(x1), "=r"(y0), "=r"(y1) : "r"(o), "r"(m));
+    b0 = x0; b1 = x1; e0 = y0; e1 = y1;
+  }
+  static __device__ __forceinline__ uint32_t splat(unsigned short v) { return (uint32_t)v | ((uint32_t)v << 16); }
+  static __device__ __forceinline__ float half_to_float(uint32_t w, int hi) {
+    return __half2float(__ushort_as_half((unsigned short)(hi ? (w >> 16) : (w & 0xffffu))));
+  }
+  static __device__ __forceinline__ uint32_t extreme(bool max_) { return max_ ? 0xFBFFFBFFu : 0x7BFF7BFFu; }  // -65504 / 65504
+};
+
+template <typename T, int RED, int LPR, int CH, int U> struct MinMax16Engine {
+  using V = Vec<T>;
+  using P = Pk<T>;
+  static constexpr int VEC = 8;
+  static constexpr int G = 32 / LPR;
+  static constexpr int NA = VEC * CH;
+  static constexpr bool ARG = true;
+  static constexpr bool MAX = (RED == R_MAX);
+
+  uint32_t pacc[NA / 2];
+  int arg[NA];
+
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < NA / 2; i++) pacc[i] = P::extreme(MAX);
+#pragma unroll
+    for (int i = 0; i < NA; i++) arg[i] = 0x7fffffff;
+  }
+  __device__ __forceinline__ float acc_float(int i) const { return P::half_to_float(pacc[i >> 1], i & 1); }
+
+  __device__ __forceinline__ void vec_step(int ch, unsigned short v, const uint4& d, int jabs) {
+    const uint32_t v2 = P::splat(v);  // 1.0 when has_value=false => exact products
+    const uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      P::template step<MAX>(pacc[ch * 4 + k], arg[ch * 8 + 2 * k], arg[ch * 8 + 2 * k + 1], P::mul(w[k], v2), jabs);
+  }
+
+  __device__ __forceinline__ void accumulate(IndexRing<T>& ring, int s, int e,
+                                             const char* __restrict__ matb, uint32_t row_bytes,
+                                             const bool (&col_ok)[CH], int lane, int g, uint64_t pol) {
+    using VR = typename V::vraw;
+    for (int j0 = s; j0 < e; j0 += U * G) {
+      const int jend = min(e, j0 + U * G);
+      ring.ensure(j0, jend, lane);
+      const int slot0 = (j0 + g) & (kRing - 1);
+      const uint32_t* pc = reinterpret_cast<const uint32_t*>(ring.s_col + slot0);
+      const VR* pv = reinterpret_cast<const VR*>(ring.s_val) + slot0;
+      const int jabs0 = (int)ring.base + j0 + g;
+      const int nst = (jend - j0 + G - 1) / G;
+      const int jrel = jend - j0 - g;
+      uint4 d[U][CH];
+      VR v[U];
+      bool act[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (u >= nst) break;
+        act[u] = u * G < jrel;
+        const uint32_t c = pc[2 * u * G];
+        v[u] = pv[u * G];
+        const char* src = matb + (uint64_t)c * row_bytes;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++)
+          if (act[u] && col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (u >= nst) break;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++)
+          if (act[u] && col_ok[ch]) vec_step(ch, v[u], d[u][ch], jabs0 + u * G);
+      }
+    }
+  }
+
+  __device__ __forceinline__ void reduce_groups() {
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+      for (int k = 0; k < NA / 2; k++) {
+        const uint32_t o = __shfl_xor_sync(0xffffffffu, pacc[k], off);
+        const int oa0 = __shfl_xor_sync(0xffffffffu, arg[2 * k], off);
+        const int oa1 = __shfl_xor_sync(0xffffffffu, arg[2 * k + 1], off);
+        bool b0, b1, e0, e1;
+        P::template cmp<MAX>(o, pacc[k], b0, b1, e0, e1);
+        const bool t0 = b0 || (e0 && oa0 < arg[2 * k]);
+        const bool t1 = b1 || (e1 && oa1 < arg[2 * k + 1]);
+        const uint32_t mask = (t0 ? 0x0000ffffu : 0u) | (t1 ? 0xffff0000u : 0u);
+        pacc[k] = (o & mask) | (pacc[k] & ~mask);
+        if (t0) arg[2 * k] = oa0;
+        if (t1) arg[2 * k + 1] = oa1;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void store_row(T* __restrict__ out_row, int64_t* __restrict__ arg_row,
+                                            int64_t count, int64_t E, const bool (&col_ok)[CH], int li, bool) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ch++) {
+      if (!col_ok[ch]) continue;
+      const int koff = (ch * LPR + li) * VEC;
+      uint4 o = make_uint4(pacc[ch * 4], pacc[ch * 4 + 1], pacc[ch * 4 + 2], pacc[ch * 4 + 3]);
+      if (count == 0) o = make_uint4(0, 0, 0, 0);
+      stg128_stream(out_row + koff, o);
+#pragma unroll
+      for (int i = 0; i < VEC; i += 2) {
+        longlong2 a2;
+        a2.x = (count > 0 && arg[ch * VEC + i] != 0x7fffffff) ? (int64_t)arg[ch * VEC + i] : E;
+        a2.y = (count > 0 && arg[ch * VEC + i + 1] != 0x7fffffff) ? (int64_t)arg[ch * VEC + i + 1] : E;
+        stg128_stream(arg_row + koff + i, *reinterpret_cast<uint4*>(&a2));
+      }
+    }
+  }
+};
+
+template <typename T, int RED, int LPR, int CH, int U> struct EngineFor {
+  using type = typename std::conditional<(RED != R_SUM && is_float16<T>::value), MinMax16Engine<T, RED, LPR, CH, U>,
+                                         RowEngine<T, RED, LPR, CH, U>>::type;
+};
+
 template <typename T, int RED, int LPR, int CH, int U, int MINB>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_vec_kernel(const SpmmParams p) {
-  using Eng = RowEngine<T, RED, LPR, CH, U>;
+  using Eng = typename EngineFor<T, RED, LPR, CH, U>::type;
   constexpr int VEC = Eng::VEC;
   __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRingAlloc];
   __shared__ __align__(16) T s_val[kWarpsPerCta][kRingAlloc];
@@ -668,7 +841,7 @@ spmm_gpr_kernel(const SpmmParams p) {
 template <typename T, int RED, int LPR, int CH, int U, int MINB>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_seg_kernel(const SpmmParams p) {
-  using Eng = RowEngine<T, RED, LPR, CH, U>;
+  using Eng = typename EngineFor<T, RED, LPR, CH, U>::type;
   constexpr int VEC = Eng::VEC;
   __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRingAlloc];
   __shared__ __align__(16) T s_val[kWarpsPerCta][kRingAlloc];
@@ -722,7 +895,7 @@ spmm_seg_kernel(const SpmmParams p) {
           const int koff = (ch * LPR + li) * VEC;
 #pragma unroll
           for (int i = 0; i < VEC; i++) {
-            pv[koff + i] = eng.acc[ch * VEC + i];
+            pv[koff + i] = eng.acc_float(ch * VEC + i);
             if (Eng::ARG) pa[koff + i] = eng.arg[ch * VEC + i] == 0x7fffffff ? p.E : (int64_t)eng.arg[ch * VEC + i];
           }
         }
