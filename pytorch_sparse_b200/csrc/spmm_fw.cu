@@ -696,10 +696,11 @@ template <> __device__ __forceinline__ unsigned short load_vraw<__half>(const __
   return __ldg(reinterpret_cast<const unsigned short*>(p));
 }
 
-template <typename T, int LPR, int U, int MINB>
+template <typename T, int RED, int LPR, int U, int MINB>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_gpr_kernel(const SpmmParams p) {
   using V = Vec<T>;
+  using Eng = typename EngineFor<T, RED, LPR, 1, U>::type;  // per-lane state + update + store of one row
   using VR = typename V::vraw;
   constexpr int VEC = V::VEC;
   constexpr int G = 32 / LPR;
@@ -774,7 +775,10 @@ spmm_gpr_kernel(const SpmmParams p) {
     asm volatile("" : "+l"(matb));
     const int64_t* __restrict__ colb = p.col + base;
     const T* __restrict__ valb = has_val ? val + base : nullptr;
-    T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0 + li * VEC;
+    T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0;
+    int64_t* argb = p.arg_out ? p.arg_out + (b * p.M + r0) * p.K + p.k0 : nullptr;
+    const bool col_ok_arr[1] = {col_ok};
+    const int jbase = (int)base;  // absolute nnz index of ring-relative 0 (E < 2^31)
 
     for (int t = 0; t < nrows; t += G) {
       const int rl = t + g;  // this lane group's row
@@ -787,9 +791,8 @@ spmm_gpr_kernel(const SpmmParams p) {
 #pragma unroll
       for (int off = LPR; off < 32; off <<= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, off));
 
-      float acc[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; i++) acc[i] = 0.f;
+      Eng eng;
+      eng.init();
 
       // software pipeline: the (col, value) pairs of chunk k+1 are loaded while chunk k's gathers fly
       uint32_t cn[U];
@@ -822,16 +825,15 @@ spmm_gpr_kernel(const SpmmParams p) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < U; u++)
-          if (act[u]) V::fma(acc, v[u], d[u]);
-      }
-      if (mine && col_ok) {
-        if (p.mean) {
-#pragma unroll
-          for (int i = 0; i < VEC; i++) acc[i] = acc[i] / (float)(len > 0 ? len : 1);
+        for (int u = 0; u < U; u++) {
+          if (!act[u]) continue;
+          if constexpr (RED == R_SUM) V::fma(eng.acc, v[u], d[u]);
+          else if constexpr (is_float16<T>::value) eng.vec_step(0, v[u], d[u], jbase + s + j0 + u);
+          else eng.minmax_step(eng.acc, eng.arg, v[u], d[u], jbase + s + j0 + u);
         }
-        stg128_stream(outb + (int64_t)rl * p.K, V::pack(acc));
       }
+      if (mine) eng.store_row(outb + (int64_t)rl * p.K, argb ? argb + (int64_t)rl * p.K : nullptr, len, p.E, col_ok_arr, li,
+                              p.mean != 0);
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
   }
@@ -1037,7 +1039,7 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int kcols = LPR * CH * VEC;
   void (*kmain)(const SpmmParams);
-  if constexpr (GPR) kmain = spmm_gpr_kernel<T, LPR, U, MINB>;
+  if constexpr (GPR) kmain = spmm_gpr_kernel<T, RED, LPR, U, MINB>;
   else kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB>;
   constexpr int USEG = (U > LPR) ? LPR : U;  // the row engine needs U * (32 / LPR) <= 32
   auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, USEG, MINB>;
@@ -1069,7 +1071,7 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
 template <typename T, int RED> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   const int64_t vecs = p.K / VEC;  // 16-byte vectors per dense row
-  if constexpr (RED == R_SUM) {  // narrow rows: group-per-row kernel (sum / mean)
+  {  // narrow rows: group-per-row kernel (all reductions)
     if (vecs <= 1) return launch_vec<T, RED, 1, 1, 4, 5, true>(p, st);
     if (vecs <= 2) return launch_vec<T, RED, 2, 1, 4, 5, true>(p, st);
     if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4, 5, true>(p, st);
