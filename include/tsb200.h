@@ -91,11 +91,15 @@ TSB200_API int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
  * SpMM value gradient (SDDMM).  Replaces spmm_value_bw -> spmm_value_bw_cpu / _cuda
  *   (csrc/spmm.cpp:37-49, csrc/cpu/spmm_cpu.cpp:103-152, csrc/cuda/spmm_cuda.cu:196-237).
  *   out[e] = sum_b <mat[b,col[e],:], grad[b,row[e],:]>   (/ max(rowcount,1) for MEAN)
- *   `row` may be NULL (it is implied by rowptr); reduce in {SUM, MEAN}.
+ *   reduce in {SUM, MEAN}. With a workspace of tsb200_spmm_value_bw_workspace_bytes(...) bytes (256 B aligned)
+ *   and B == 1 the row-wise kernel is used (grad row in registers, only `mat` rows gathered, long rows split
+ *   through a device-side segment queue); workspace == NULL selects the nnz-parallel kernel. Same results.
  * ------------------------------------------------------------------------------------------ */
+TSB200_API size_t tsb200_spmm_value_bw_workspace_bytes(int64_t B, int64_t M, int64_t K, int64_t E, int dtype);
 TSB200_API int tsb200_spmm_value_bw(const int64_t* row, const int64_t* rowptr, const int64_t* col,
                          const void* mat, const void* grad, void* out, int64_t B, int64_t M,
-                         int64_t N, int64_t K, int64_t E, int dtype, int reduce, void* stream);
+                         int64_t N, int64_t K, int64_t E, int dtype, int reduce, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused min/max backward.  Replaces the ATen chain in SPMMMin/SPMMMax::backward

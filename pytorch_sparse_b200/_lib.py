@@ -22,8 +22,10 @@ SIGNATURES = {
     "tsb200_spmm_fw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
                                c_void_p, c_size_t, c_void_p]),
+    "tsb200_spmm_value_bw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),
     "tsb200_spmm_value_bw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+                                     c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
+                                     c_void_p, c_size_t, c_void_p]),
     "tsb200_spmm_minmax_bw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "tsb200_ind2ptr": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

@@ -10,7 +10,7 @@
 //  * tsb200_spmm_minmax_bw: fused replacement of the 8-op ATen chain of SPMMMin/SPMMMax::backward
 //    (csrc/spmm.cpp:204-242, 264-302): one pass over arg_out, atomics into zero-filled fp32/fp64
 //    accumulators.
-#include "common.cuh"
+#include "spmm_common.cuh"
 
 namespace tsb {
 
@@ -154,6 +154,221 @@ value_bw_vec_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__
   }
 }
 
+// ---- row-wise SDDMM (B == 1) ---------------------------------------------------------------------
+// Same work decomposition as the SpMM forward (spmm_fw.cu): a warp pulls 32-row items from an atomic
+// counter, the item's column indices stream through the per-warp cp.async ring, rows that are too long
+// (or overflow the item's nnz budget) are deferred as <= 256-nnz segments to a second kernel. Per row the
+// grad vector is loaded ONCE into registers (16 B per lane and chunk), so only the dense-operand rows are
+// gathered (half the L1/L2 traffic of the nnz-parallel kernel); every nnz's dot product is reduced over the
+// LPR lanes with the halving butterfly and the chunk's results leave with one coalesced store.
+template <typename T, int LPR, int CH, int U> struct SddmmEngine {
+  static constexpr int VEC = 16 / sizeof(T);
+  static constexpr int G = 32 / LPR;
+  uint4 gq[CH];
+
+  __device__ __forceinline__ void load_grad(const char* grad_row, const bool (&col_ok)[CH], int li) {
+#pragma unroll
+    for (int ch = 0; ch < CH; ch++)
+      gq[ch] = col_ok[ch] ? ldg128(grad_row + (ch * LPR + li) * 16) : make_uint4(0, 0, 0, 0);
+  }
+
+  // ring-relative nnz [s, e) of one row -> out[absolute nnz]
+  __device__ __forceinline__ void run(IndexRing<T>& ring, int s, int e, const char* __restrict__ matb,
+                                      uint32_t row_bytes, const bool (&col_ok)[CH], int lane, int g, int li,
+                                      uint64_t pol, T* __restrict__ out, float scale) {
+    for (int j0 = s; j0 < e; j0 += U * G) {
+      const int jend = min(e, j0 + U * G);
+      ring.ensure(j0, jend, lane);
+      const int slot0 = (j0 + g) & (kRing - 1);
+      const uint32_t* pc = reinterpret_cast<const uint32_t*>(ring.s_col + slot0);
+      const int nst = (jend - j0 + G - 1) / G;
+      const int jrel = jend - j0 - g;
+      uint4 d[U][CH];
+      bool act[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        act[u] = (u < nst) && (u * G < jrel);
+        if (act[u]) {
+          const uint32_t c = pc[2 * u * G];
+          const char* src = matb + (uint64_t)c * row_bytes;
+#pragma unroll
+          for (int ch = 0; ch < CH; ch++)
+            if (col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
+        }
+      }
+      float part[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float sdot = 0.f;
+        if (act[u]) {
+#pragma unroll
+          for (int ch = 0; ch < CH; ch++)
+            if (col_ok[ch]) sdot += Vec16<T, VEC>::dot(d[u][ch], gq[ch]);
+        }
+        part[u] = sdot;
+      }
+      // lane li of group g gets the total of step li / (LPR/U); nnz t = u*G + g of the chunk goes to lane t
+      const float tot = multi_reduce<U, LPR / 2>(part, li);
+      const bool mine = lane < jend - j0;
+      const int src_lane = mine ? (lane % G) * LPR + (lane / G) * (LPR / U) : 0;
+      const float got = __shfl_sync(0xffffffffu, tot, src_lane);
+      if (mine) out[ring.base + j0 + lane] = Traits<T>::from_acc(got * scale);
+    }
+  }
+};
+
+template <typename T, int LPR, int CH, int U, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
+sddmm_vec_kernel(const SpmmParams p, const T* __restrict__ grad, T* __restrict__ out) {
+  using Eng = SddmmEngine<T, LPR, CH, U>;
+  constexpr int VEC = Eng::VEC;
+  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRingAlloc];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LPR, li = lane % LPR;
+
+  IndexRing<T> ring;
+  ring.s_col = s_col[warp];
+  ring.s_val = nullptr;
+  ring.has_val = false;
+  ring.col = p.col;
+  ring.val = nullptr;
+  ring.limit = p.E;
+  const uint64_t pol = make_policy_evict_last();
+
+  bool col_ok[CH];
+#pragma unroll
+  for (int ch = 0; ch < CH; ch++) col_ok[ch] = (ch * LPR + li) * VEC < p.K;
+  const uint32_t row_bytes = (uint32_t)(p.K * (int64_t)sizeof(T));
+  const char* matb = (const char*)p.mat + (int64_t)li * 16;
+  asm volatile("" : "+l"(matb));
+
+  const int item_rows = 1 << p.item_shift;
+  const int64_t n_items = (p.M + item_rows - 1) >> p.item_shift;
+  unsigned int item = 0;
+  if (lane == 0) item = atomicAdd(&p.counters[0], 1u);
+  item = __shfl_sync(0xffffffffu, item, 0);
+
+  while ((int64_t)item < n_items) {
+    unsigned int next_item = 0;
+    if (lane == 0) next_item = atomicAdd(&p.counters[0], 1u);
+    const int64_t r0 = (int64_t)item << p.item_shift;
+    const int nrows = (int)min((int64_t)item_rows, p.M - r0);
+    const int64_t rp0 = __ldg(p.rowptr + r0 + min(lane, nrows));
+    const int64_t rp1 = __ldg(p.rowptr + r0 + min(lane + 1, nrows));
+    const int64_t a0 = __shfl_sync(0xffffffffu, rp0, 0);
+    const int64_t base = a0 & ~(int64_t)31;
+    const int s_rel = (int)(rp0 - base), e_rel = (int)(rp1 - base);
+    const int deg = e_rel - s_rel;
+    const bool is_long = deg > kLongT;
+    int cum = is_long ? 0 : deg;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, cum, off);
+      if (lane >= off) cum += t;
+    }
+    const bool defer = (deg > 0) && (is_long || cum > kItemCap);
+    const unsigned defer_mask = __ballot_sync(0xffffffffu, defer);
+    if (defer) {
+      const int nseg = (deg + kSeg - 1) / kSeg;
+      const unsigned seg0 = atomicAdd(&p.counters[1], (unsigned)nseg);
+      for (int sgi = 0; sgi < nseg; sgi++) {
+        if ((int64_t)seg0 + sgi < p.seg_cap) {
+          Segment S;
+          S.row_b = r0 + lane;
+          S.start = rp0 + (int64_t)sgi * kSeg;
+          S.end = min(rp1, S.start + kSeg);
+          S.slot = -1;
+          p.segs[seg0 + sgi] = S;
+        }
+      }
+    }
+    __syncwarp();
+    ring.reset(base, __shfl_sync(0xffffffffu, rp1, 31));
+    for (int rl = 0; rl < nrows; rl++) {
+      if ((defer_mask >> rl) & 1u) continue;
+      const int s = __shfl_sync(0xffffffffu, s_rel, rl);
+      const int e = __shfl_sync(0xffffffffu, e_rel, rl);
+      if (e == s) continue;
+      Eng eng;
+      eng.load_grad((const char*)grad + (r0 + rl) * (int64_t)row_bytes, col_ok, li);
+      const float scale = p.mean ? 1.f / (float)(e - s) : 1.f;
+      eng.run(ring, s, e, matb, row_bytes, col_ok, lane, g, li, pol, out, scale);
+    }
+    item = __shfl_sync(0xffffffffu, next_item, 0);
+  }
+}
+
+template <typename T, int LPR, int CH, int U, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
+sddmm_seg_kernel(const SpmmParams p, const T* __restrict__ grad, T* __restrict__ out) {
+  using Eng = SddmmEngine<T, LPR, CH, U>;
+  constexpr int VEC = Eng::VEC;
+  __shared__ __align__(16) int64_t s_col[kWarpsPerCta][kRingAlloc];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LPR, li = lane % LPR;
+  IndexRing<T> ring;
+  ring.s_col = s_col[warp];
+  ring.s_val = nullptr;
+  ring.has_val = false;
+  ring.col = p.col;
+  ring.val = nullptr;
+  ring.limit = p.E;
+  const uint64_t pol = make_policy_evict_last();
+  bool col_ok[CH];
+#pragma unroll
+  for (int ch = 0; ch < CH; ch++) col_ok[ch] = (ch * LPR + li) * VEC < p.K;
+  const uint32_t row_bytes = (uint32_t)(p.K * (int64_t)sizeof(T));
+  const char* matb = (const char*)p.mat + (int64_t)li * 16;
+  asm volatile("" : "+l"(matb));
+
+  const int64_t nseg = min((int64_t)p.counters[1], p.seg_cap);
+  const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
+  for (int64_t sidx = (int64_t)blockIdx.x * kWarpsPerCta + warp; sidx < nseg; sidx += wstride) {
+    const Segment S = p.segs[sidx];
+    const int64_t base = S.start & ~(int64_t)31;
+    ring.reset(base, S.end);
+    Eng eng;
+    eng.load_grad((const char*)grad + S.row_b * (int64_t)row_bytes, col_ok, li);
+    float scale = 1.f;
+    if (p.mean) {
+      const int64_t cnt = __ldg(p.rowptr + S.row_b + 1) - __ldg(p.rowptr + S.row_b);
+      scale = 1.f / (float)(cnt > 0 ? cnt : 1);
+    }
+    eng.run(ring, (int)(S.start - base), (int)(S.end - base), matb, row_bytes, col_ok, lane, g, li, pol, out, scale);
+    __syncwarp();
+  }
+}
+
+template <typename T, int LPR, int CH, int U, int MINB>
+static int launch_sddmm(SpmmParams p, const void* grad, void* out, cudaStream_t st) {
+  auto* kmain = sddmm_vec_kernel<T, LPR, CH, U, MINB>;
+  auto* kseg = sddmm_seg_kernel<T, LPR, CH, U, MINB>;
+  static int grid_main = 0, grid_seg = 0;
+  if (!grid_main) grid_main = grid_for((const void*)kmain, kWarpsPerCta * 32);
+  if (!grid_seg) grid_seg = grid_for((const void*)kseg, kWarpsPerCta * 32);
+  int64_t want = p.M / ((int64_t)grid_main * kWarpsPerCta * 2);
+  p.item_shift = 0;
+  while (p.item_shift < 5 && ((int64_t)2 << p.item_shift) <= want) p.item_shift++;
+  const int64_t n_items = (p.M + (1 << p.item_shift) - 1) >> p.item_shift;
+  TSB_CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));
+  const int gm = (int)min((int64_t)grid_main, (n_items + kWarpsPerCta - 1) / kWarpsPerCta);
+  kmain<<<gm, kWarpsPerCta * 32, 0, st>>>(p, (const T*)grad, (T*)out);
+  TSB_LAUNCH_CHECK();
+  kseg<<<grid_seg, kWarpsPerCta * 32, 0, st>>>(p, (const T*)grad, (T*)out);
+  TSB_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T> static int dispatch_sddmm(const SpmmParams& p, const void* grad, void* out, cudaStream_t st) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int64_t vecs = p.K / VEC;
+  if (vecs <= 4) return launch_sddmm<T, 4, 1, 4, 5>(p, grad, out, st);
+  if (vecs <= 8) return launch_sddmm<T, 8, 1, 4, 5>(p, grad, out, st);
+  if (vecs <= 16) return launch_sddmm<T, 16, 1, 4, 5>(p, grad, out, st);
+  if (vecs <= 32) return launch_sddmm<T, 32, 1, 4, 4>(p, grad, out, st);
+  return launch_sddmm<T, 32, 2, 4, 3>(p, grad, out, st);  // up to 64 vectors
+}
+
 // generic: warp per nnz, lanes stride over k (any dtype / alignment).
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -238,9 +453,17 @@ static int dispatch_value_vec(const int64_t* row, const int64_t* rowptr, const i
 
 using namespace tsb;
 
+extern "C" size_t tsb200_spmm_value_bw_workspace_bytes(int64_t B, int64_t M, int64_t K, int64_t E, int dtype) {
+  (void)M;
+  if (dtype != TSB200_F32 && dtype != TSB200_F16 && dtype != TSB200_BF16) return 0;
+  if (B != 1 || K <= 0 || E <= 0) return 0;
+  return ws_layout(1, K, E, false, false).total;
+}
+
 extern "C" int tsb200_spmm_value_bw(const int64_t* row, const int64_t* rowptr, const int64_t* col,
                                     const void* mat, const void* grad, void* out, int64_t B, int64_t M,
-                                    int64_t N, int64_t K, int64_t E, int dtype, int reduce, void* stream) {
+                                    int64_t N, int64_t K, int64_t E, int dtype, int reduce, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
   if (B < 0 || M < 0 || N < 0 || K < 0 || E < 0) return TSB200_ERR_INVALID_ARG;
   if (reduce != TSB200_SUM && reduce != TSB200_MEAN) return TSB200_ERR_INVALID_ARG;
   if (dtype_size(dtype) == 0) return TSB200_ERR_INVALID_ARG;
@@ -253,6 +476,28 @@ extern "C" int tsb200_spmm_value_bw(const int64_t* row, const int64_t* rowptr, c
   const bool vec = (dtype == TSB200_F32 || dtype == TSB200_F16 || dtype == TSB200_BF16) && K > 0 &&
                    (K * es) % 16 == 0 && !((uintptr_t)mat & 15) && !((uintptr_t)grad & 15) &&
                    M < ((int64_t)1 << 32) && N < ((int64_t)1 << 32) && K * (int64_t)es < ((int64_t)1 << 31);
+  // row-wise path: single batch, >= 4 and <= 64 vectors per dense row, a workspace for the segment queue
+  const int64_t vecs = vec ? (K * (int64_t)es) / 16 : 0;
+  if (vec && B == 1 && vecs >= 3 && vecs <= 64 && E < ((int64_t)1 << 31) - 64 && !((uintptr_t)col & 7) && workspace &&
+      !((uintptr_t)workspace & 255)) {
+    const WsLayout L = ws_layout(1, K, E, false, false);
+    if (workspace_bytes >= L.total) {
+      char* ws = (char*)workspace;
+      SpmmParams p;
+      p.rowptr = rowptr; p.col = col; p.value = nullptr; p.mat = mat; p.out = nullptr; p.arg_out = nullptr;
+      p.B = 1; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = mean ? 1 : 0; p.item_shift = 5;
+      p.counters = (unsigned int*)(ws + L.counters);
+      p.segs = (Segment*)(ws + L.segs);
+      p.longs = (LongRow*)(ws + L.longs);
+      p.part_val = nullptr; p.part_arg = nullptr;
+      p.seg_cap = L.seg_cap; p.long_cap = L.long_cap; p.slot_cap = L.slot_cap;
+      switch (dtype) {
+        case TSB200_F32: return dispatch_sddmm<float>(p, grad, out, st);
+        case TSB200_F16: return dispatch_sddmm<__half>(p, grad, out, st);
+        case TSB200_BF16: return dispatch_sddmm<__nv_bfloat16>(p, grad, out, st);
+      }
+    }
+  }
   if (vec) {
     switch (dtype) {
       case TSB200_F32: return dispatch_value_vec<float>(row, rowptr, col, mat, grad, out, B, M, N, K, E, mean, st);

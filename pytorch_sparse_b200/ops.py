@@ -156,8 +156,11 @@ def spmm_value_bw(row: Tensor, rowptr: Tensor, col: Tensor, mat: Tensor, grad: T
     if E == 0 or B * K == 0:
         return out
     with _on_device(dev):
+        dt = _dtype_code(mat.dtype)
+        nws = lib.tsb200_spmm_value_bw_workspace_bytes(B, M, K, E, dt)
+        ws = _workspace(nws, dev)
         check(lib.tsb200_spmm_value_bw(_p(row), _p(rowptr), _p(col), _p(mat), _p(grad), _p(out),
-                                       B, M, N, K, E, _dtype_code(mat.dtype), red, _stream(dev)),
+                                       B, M, N, K, E, dt, red, _p(ws), nws, _stream(dev)),
               "tsb200_spmm_value_bw")
     return out
 

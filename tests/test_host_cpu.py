@@ -36,7 +36,7 @@ def test_argument_validation_without_gpu():
     assert lib.tsb200_spmm_fw_workspace_bytes(1, 1000, 128, 16000, 3, 0) > 0
     assert lib.tsb200_spmm_fw_workspace_bytes(1, 1000, 128, 16000, 5, 0) == 0      # int64: generic kernel
     assert lib.tsb200_coalesce_workspace_bytes(1000, 10, 10) > 16 * 1000
-    assert lib.tsb200_spmm_value_bw(None, None, None, None, None, None, 1, 4, 4, 4, 4, 0, 2, None) == -1  # reduce=min
+    assert lib.tsb200_spmm_value_bw(None, None, None, None, None, None, 1, 4, 4, 4, 4, 0, 2, None, 0, None) == -1  # reduce=min
 
 
 def test_ops_reject_cpu_tensors():
