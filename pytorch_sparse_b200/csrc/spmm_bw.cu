@@ -10,6 +10,8 @@
 //  * tsb200_spmm_minmax_bw: fused replacement of the 8-op ATen chain of SPMMMin/SPMMMax::backward
 //    (csrc/spmm.cpp:204-242, 264-302): one pass over arg_out, atomics into zero-filled fp32/fp64
 //    accumulators.
+#include <cstdlib>
+
 #include "spmm_common.cuh"
 
 namespace tsb {
@@ -400,24 +402,37 @@ value_bw_generic_kernel(const int64_t* __restrict__ row, const int64_t* __restri
   }
 }
 
+// Fused min/max backward (csrc/spmm.cpp:204-242 as ONE pass over arg_out): every output element (r, k) routes
+// grad_out[r, k] to value[arg] and to grad_mat[col[arg], k]. The scattered 4-byte reads of mat and atomics on
+// grad_mat touch one 32-byte sector each; with both arrays far larger than L2 (C3: 512 MB each) every sector would
+// be fetched from / written back to DRAM up to 8 times (~13 GB of traffic for 2 GB of data). So the element space
+// is walked FEATURE-SLICE-major by a persistent grid: all CTAs work on the same 2^lsl-feature slice at the same
+// time, and a slice of mat + grad_mat (N * 2^lsl * (s + 4) bytes, sized by the host to ~32 MB) stays L2-resident
+// while the whole arg_out / grad_out slice streams through -- each DRAM byte moves once.
 template <typename T, typename A>
 __global__ void __launch_bounds__(256)
 minmax_bw_kernel(const int64_t* __restrict__ col, const T* __restrict__ value, const T* __restrict__ mat,
                  const T* __restrict__ grad_out, const int64_t* __restrict__ arg_out,
                  A* __restrict__ grad_value, A* __restrict__ grad_mat, int64_t B, int64_t M, int64_t N,
-                 int64_t K, int64_t E) {
-  const int64_t total = B * M * K;
+                 int64_t K, int64_t E, int lsl) {
+  const int64_t per_slice = (B * M) << lsl;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t a = arg_out[i];
-    if (a < 0 || a >= E) continue;  // sentinel E: empty row (csrc/spmm.cpp:270-271)
-    const int64_t k = i % K;
-    const int64_t b = i / (M * K);
-    const A g = (A)Traits<T>::to_acc(grad_out[i]);
-    const int64_t c = col[a];
-    const int64_t mi = (b * N + c) * K + k;
-    if (grad_value) atomicAdd(grad_value + a, (A)Traits<T>::to_acc(mat[mi]) * g);
-    if (grad_mat) atomicAdd(grad_mat + mi, value ? (A)Traits<T>::to_acc(value[a]) * g : g);
+  const int64_t kmask = ((int64_t)1 << lsl) - 1;
+  for (int64_t k0 = 0; k0 < K; k0 += kmask + 1) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < per_slice; j += stride) {
+      const int64_t r = j >> lsl;
+      const int64_t k = k0 + (j & kmask);
+      if (k >= K) continue;
+      const int64_t i = r * K + k;
+      const int64_t a = arg_out[i];
+      if (a < 0 || a >= E) continue;  // sentinel E: empty row (csrc/spmm.cpp:270-271)
+      const A g = (A)Traits<T>::to_acc(grad_out[i]);
+      const int64_t c = col[a];
+      const int64_t b = B == 1 ? 0 : r / M;
+      const int64_t mi = (b * N + c) * K + k;
+      if (grad_value) atomicAdd(grad_value + a, (A)Traits<T>::to_acc(mat[mi]) * g);
+      if (grad_mat) atomicAdd(grad_mat + mi, value ? (A)Traits<T>::to_acc(value[a]) * g : g);
+    }
   }
 }
 
@@ -528,15 +543,40 @@ extern "C" int tsb200_spmm_minmax_bw(const int64_t* col, const void* value, cons
   if (grad_value && !mat) return TSB200_ERR_INVALID_ARG;
   if (!grad_value && !grad_mat) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = B * M * K;
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)kNumSMs * 32;
-  if (blocks > cap) blocks = cap;
   return dispatch_float_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     using A = typename std::conditional<std::is_same<T, double>::value, double, float>::type;
-    minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
-                                                       arg_out, (A*)grad_value, (A*)grad_mat, B, M, N, K, E);
+    // feature slice: largest power of two whose mat / grad_mat columns fit the L2 budget; never narrower than one
+    // 128-byte L2 line (L2 capacity is counted in LINES: a slice using one 32-byte sector of each line would
+    // occupy four times its size)
+    int full = 0;
+    while (((int64_t)1 << full) < K) full++;  // whole rows when everything fits
+    const int min_lsl = sizeof(T) >= 8 ? 4 : (sizeof(T) >= 4 ? 5 : 6);
+    int lsl = full;
+    const double per_feature = (double)B * (double)N * (double)sizeof(A);
+    while (lsl > min_lsl && per_feature * (double)((int64_t)1 << lsl) > 40.0 * 1024 * 1024) lsl--;
+    // with both gradients requested the mat slice (read) and the grad_mat slice (atomics) would have to share L2:
+    // run two passes, each with one resident slice, unless a whole-row walk fits anyway
+    bool split = grad_value && grad_mat && lsl < full;
+    if (const char* ev = getenv("TSB200_MMBW_LSL")) { lsl = atoi(ev); if (lsl > full) lsl = full; if (lsl < 0) lsl = 0; }
+    if (const char* ev = getenv("TSB200_MMBW_SPLIT")) split = atoi(ev) != 0 && grad_value && grad_mat;
+    // persistent grid: every CTA resident, so all of them walk the slices in step
+    int per_sm = 8;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)minmax_bw_kernel<T, A>, 256, 0);
+    if (per_sm < 1) per_sm = 1;
+    int64_t blocks = ((B * M << lsl) + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (split) {
+      minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
+                                                         arg_out, (A*)nullptr, (A*)grad_mat, B, M, N, K, E, lsl);
+      TSB_LAUNCH_CHECK();
+      minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
+                                                         arg_out, (A*)grad_value, (A*)nullptr, B, M, N, K, E, lsl);
+    } else {
+      minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
+                                                         arg_out, (A*)grad_value, (A*)grad_mat, B, M, N, K, E, lsl);
+    }
     TSB_LAUNCH_CHECK();
     return 0;
   });

@@ -5,16 +5,30 @@
 // structural (numerical zeros are kept).
 //
 // Two-phase row-wise Gustavson with a per-CTA shared-memory BITMAP accumulator:
-//   * a CTA owns one output row at a time (rows are pulled from a global atomic counter);
-//   * every product a_ik * b_kj sets bit j of a bitmap over a window of <= 2^19 columns
-//     (64 KB); a 2-level summary bitmap remembers which 32-bit words were touched, so counting,
-//     ranking and clearing only visit touched words;
-//   * popcounts of the bitmap give (symbolic) the row's nnz and (numeric) the rank of every
-//     column => the output row is produced ALREADY SORTED by column, with no per-row sort and
-//     no hash probing; values are accumulated with shared-memory atomics at their rank
-//     (global atomics for rows wider than the shared accumulator);
-//   * matrices wider than one window are processed window by window (B rows are column-sorted,
-//     so only windows between the row's smallest and largest product column are visited).
+//   * a CTA owns one output row at a time (rows are handed out in chunks of 8 from a global atomic
+//     counter; the chunk's rowptr entries and the next row's A-row metadata are prefetched so the
+//     dependent global loads rowptr_a -> col_a -> rowptr_b of row r+1 overlap the work of row r);
+//   * every product a_ik * b_kj sets bit j of a bitmap over a window of <= 2^18 columns (32 KB, XOR-swizzled
+//     so that a thread can scan "its" 32 words with conflict-free LDS.128);
+//   * one dense pass turns the bitmap into ranks (thread t owns words [32t, 32t+32): 8 x LDS.128 + popc,
+//     one block scan): rank of column j = group prefix + popc(bits below j) => the output row comes out
+//     ALREADY SORTED by column with no per-row sort and no hash probing;
+//   * FLAT rows (single window, <= 128 A entries, <= 2048 products; every row of BASELINE's C4): the row's
+//     products are numbered 0..P-1 through a prefix sum of the B-row lengths and dealt to the threads
+//     (chunks of 32 round-robin over the warps, <= 8 products per thread), which keep them in REGISTERS across the passes, so B is read once per phase and every lane
+//     is busy whatever the B-row lengths are. Bits are set with plain LDS/STS (shared-memory atomics cost
+//     2 cycles PER LANE on sm_100: 64 cycles per scattered warp-wide ATOMS.OR, 1.9 ms per pass at C4);
+//     two writers racing on one WORD can lose a bit, so after a barrier every product checks its own bit
+//     and repairs a loss with an atomicOr (atomics only add bits, so the repair pass is race-free and only
+//     the rare losers pay). The output row is staged in shared memory -- one word per slot carries the
+//     column and the id of the product that wrote it last (= the slot's owner, which stores its value; the
+//     rare other products of that column add theirs after a barrier) -- and leaves the SM as fully
+//     coalesced streaming stores of row / col / val;
+//   * other rows (GENERAL path) re-walk their products per pass (warp per A entry, lanes striding the B
+//     row), window by window for matrices wider than one window (B rows are column-sorted, so only windows
+//     between the row's smallest and largest product column are visited); bits via atomicOr, whose return
+//     value tells the product whether it was the first on its column (the symbolic pass just counts those),
+//     values with L2 atomics straight into val_c.
 // Everything is HBM-bound on the 16+s bytes per output nonzero that must be written.
 #include <cstdlib>
 
@@ -25,22 +39,63 @@
 namespace tsb {
 
 constexpr int kSpThreads = 256;
-constexpr int kAccCap = 4096;         // shared accumulator entries per window
-constexpr int kMaxWindowBits = 1 << 19;
+constexpr int kSpWarps = kSpThreads / 32;
+constexpr int kFlatU = 8;                         // products per thread on the flat path
+constexpr int kStageCap = kFlatU * kSpThreads;    // output entries staged in shared memory per row (2048)
+constexpr int kMaxWindowLog2 = 18;
+constexpr int kMaxWindowBits = 1 << kMaxWindowLog2;
+constexpr int kRowsPerGrab = 8;                   // rows handed to a CTA per atomic
+constexpr int kABatch = 128;                      // A entries staged per batch
+static_assert(kStageCap <= (1 << (32 - kMaxWindowLog2 - 1)), "owner id and column share one 32-bit word");
 
 struct SpParams {
   const int64_t* rowptr_a; const int64_t* col_a; const void* val_a;
   const int64_t* rowptr_b; const int64_t* col_b; const void* val_b;
   int64_t M, Kd, N;
-  int64_t* counts;          // symbolic: per-row nnz (written at rowptr_c + 1)
+  int64_t* counts;          // symbolic: per-row nnz (accumulated at rowptr_c + 1, pre-zeroed)
   const int64_t* rowptr_c;  // numeric
   int64_t* row_c; int64_t* col_c; void* val_c;
   unsigned int* counter;
-  int window_bits;  // power of two, >= 1024
-  int acc_cap;      // entries of the shared-memory value accumulator (0: accumulate with global atomics)
+  int window_bits;  // power of two, 1024 .. 2^18
+  int log2_wpt;     // log2(bitmap words per scan chunk), 2..5; chunks = (window_bits/32) >> log2_wpt <= 256
 };
 
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
+// bitmap word -> shared-memory word: XOR swizzle of the 16-byte group index inside each 32-word block with the
+// block index, so that thread t reading group g of block t (chunk scans) is conflict-free without padding
+__device__ __forceinline__ uint32_t sp_phys(uint32_t w) { return w ^ (((w >> 5) & 7u) << 2); }
+
+__device__ __forceinline__ int popc4(const uint4 q) { return __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w); }
+
+// plain (non-atomic) bit set + repair, see the header comment
+__device__ __forceinline__ void sp_mark(uint32_t* bitmap, uint32_t c0) {
+  volatile uint32_t* a = bitmap + sp_phys(c0 >> 5);
+  const uint32_t old = *a;
+  *a = old | (1u << (c0 & 31u));
+}
+__device__ __forceinline__ void sp_verify(uint32_t* bitmap, uint32_t c0) {
+  uint32_t* a = bitmap + sp_phys(c0 >> 5);
+  const uint32_t bit = 1u << (c0 & 31u);
+  if (!(*(volatile uint32_t*)a & bit)) atomicOr(a, bit);
+}
+
+// Rank (position in the sorted output row of this window) of window-relative column c0.
+// ABS: pre4 holds absolute 16-bit prefixes (flat rows, <= 2048 outputs); otherwise chunk-relative + tbase.
+template <bool ABS>
+__device__ __forceinline__ uint32_t sp_rank(const uint32_t* bitmap, const uint16_t* pre4, const uint32_t* tbase,
+                                            int lw, uint32_t c0) {
+  const uint32_t w = c0 >> 5, g = w >> 2, k = w & 3u;
+  const uint4 q = *reinterpret_cast<const uint4*>(&bitmap[sp_phys(g << 2)]);
+  uint32_t below = 0, word = q.x;
+  if (k > 0) { below += __popc(q.x); word = q.y; }
+  if (k > 1) { below += __popc(q.y); word = q.z; }
+  if (k > 2) { below += __popc(q.z); word = q.w; }
+  uint32_t r = pre4[g] + below + __popc(word & ((1u << (c0 & 31u)) - 1u));
+  if (!ABS) r += tbase[w >> lw];
+  return r;
+}
+
+// Block-wide exclusive scan of one int per thread, ONE barrier; `total` = sum over the CTA.
+__device__ __forceinline__ int sp_block_scan(int v, int* s_warp, int& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int x = v;
 #pragma unroll
@@ -50,245 +105,396 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& tot
   }
   if (lane == 31) s_warp[warp] = x;
   __syncthreads();
-  if (warp == 0) {
-    int w = lane < (kSpThreads / 32) ? s_warp[lane] : 0;
+  int woff = 0;
+  total = 0;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, w, off);
-      if (lane >= off) w += t;
-    }
-    if (lane < (kSpThreads / 32)) s_warp[lane] = w;  // inclusive warp totals
+  for (int w = 0; w < kSpWarps; w++) {
+    const int t = s_warp[w];
+    if (w < warp) woff += t;
+    total += t;
   }
-  __syncthreads();
-  const int warp_off = warp ? s_warp[warp - 1] : 0;
-  total = s_warp[kSpThreads / 32 - 1];
-  const int r = warp_off + x - v;
-  __syncthreads();
-  return r;
+  return woff + x - v;
 }
 
-// Per output row the CTA first stages the A-row metadata in shared memory (for each a_ik: start and
-// length of row k of B, and a_ik), ONCE; the product walks (mark, accumulate) then run warp-per-A-entry
-// with lanes striding the B row: the only global loads of a walk are the independent, coalesced reads
-// of B's column (and value) arrays — one L2/DRAM latency per walk instead of one per A entry.
-constexpr int kABatch = kSpThreads;  // A entries staged per batch
+// Dense rank pass, thread t owns chunk t (2^lw words = 2^(lw-2) groups of 4 words).
+// ABS: every chunk is read, pre4 = absolute prefix per group (16 bit). Otherwise: only chunks whose touch flag
+// is set are read, pre4 = prefix inside the chunk, tbase = exclusive prefix of the chunk.
+// Returns the number of set bits. One barrier inside; the caller must barrier before sp_rank().
+template <bool ABS>
+__device__ __forceinline__ int sp_scan(const uint32_t* bitmap, uint16_t* pre4, uint32_t* tbase,
+                                       const unsigned char* tflag, int lw, uint32_t nch, int* s_warp) {
+  const int tid = threadIdx.x;
+  const bool mine = (uint32_t)tid < nch && (ABS || tflag[tid]);
+  const uint32_t w0 = mine ? (uint32_t)tid << lw : 0u;
+  int total;
+  if (lw == 5) {
+    int c[8];
+    int run = 0;
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+      c[g] = mine ? popc4(*reinterpret_cast<const uint4*>(&bitmap[sp_phys(w0 + 4 * g)])) : 0;
+      run += c[g];
+    }
+    const int base = sp_block_scan(run, s_warp, total);
+    if (mine) {
+      int r = ABS ? base : 0;
+      uint32_t pk[4];
+#pragma unroll
+      for (int g = 0; g < 8; g += 2) {
+        pk[g >> 1] = (uint32_t)r | ((uint32_t)(r + c[g]) << 16);
+        r += c[g] + c[g + 1];
+      }
+      *reinterpret_cast<uint4*>(pre4 + (w0 >> 2)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    if (!ABS && (uint32_t)tid < nch) tbase[tid] = (uint32_t)base;
+  } else {
+    const int ng = 1 << (lw - 2);
+    int run = 0;
+    if (mine)
+      for (int g = 0; g < ng; g++) run += popc4(*reinterpret_cast<const uint4*>(&bitmap[sp_phys(w0 + 4 * g)]));
+    const int base = sp_block_scan(run, s_warp, total);
+    if (mine) {
+      int r = ABS ? base : 0;
+      for (int g = 0; g < ng; g++) {
+        pre4[(w0 >> 2) + g] = (uint16_t)r;
+        r += popc4(*reinterpret_cast<const uint4*>(&bitmap[sp_phys(w0 + 4 * g)]));
+      }
+    }
+    if (!ABS && (uint32_t)tid < nch) tbase[tid] = (uint32_t)base;
+  }
+  return total;
+}
+
+// count the set bits of (and clear) the chunk this thread owns
+__device__ __forceinline__ int sp_count_clear_chunk(uint32_t* bitmap, int lw) {
+  const uint32_t w0 = (uint32_t)threadIdx.x << lw;
+  const int ng = 1 << (lw - 2);
+  int cnt = 0;
+  if (lw == 5) {
+#pragma unroll
+    for (int g = 0; g < 8; g++) {
+      uint4* qp = reinterpret_cast<uint4*>(&bitmap[sp_phys(w0 + 4 * g)]);
+      cnt += popc4(*qp);
+      *qp = make_uint4(0, 0, 0, 0);
+    }
+  } else {
+    for (int g = 0; g < ng; g++) {
+      uint4* qp = reinterpret_cast<uint4*>(&bitmap[sp_phys(w0 + 4 * g)]);
+      cnt += popc4(*qp);
+      *qp = make_uint4(0, 0, 0, 0);
+    }
+  }
+  return cnt;
+}
 
 template <bool NUMERIC, typename T>
-__global__ void __launch_bounds__(kSpThreads) spspmm_kernel(const SpParams p) {
+__global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 4) spspmm_kernel(const SpParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  const int WW = p.window_bits >> 5;  // bitmap words
-  const int NSW = WW >> 5;            // summary words
-  uint32_t* bitmap = (uint32_t*)smem;
-  uint32_t* summary = bitmap + WW;
-  uint32_t* base = summary + NSW;                  // NUMERIC only
-  uint16_t* pre16 = (uint16_t*)(base + NSW);       // NUMERIC only
-  T* acc = (T*)(pre16 + WW);                       // NUMERIC only (16 B aligned: WW*2 is a multiple of 64)
-  __shared__ int s_warp[kSpThreads / 32];
-  __shared__ unsigned int s_row;
+  const uint32_t WW = (uint32_t)p.window_bits >> 5;   // bitmap words (>= 32)
+  const int lw = p.log2_wpt;
+  const uint32_t NCH = WW >> lw;                        // scan chunks (<= 256)
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(smem);
+  uint16_t* pre4 = reinterpret_cast<uint16_t*>(bitmap + WW);        // NUMERIC: WW/4 entries
+  uint32_t* scol = reinterpret_cast<uint32_t*>(pre4 + (WW >> 2));   // NUMERIC: kStageCap entries
+  T* acc = reinterpret_cast<T*>(scol + kStageCap);                  // NUMERIC: kStageCap entries (flat path)
+  uint32_t* tbase = reinterpret_cast<uint32_t*>(acc);               // NUMERIC: 256 entries (general path, aliases acc)
+  __shared__ int s_warp[kSpWarps];
+  __shared__ unsigned int s_chunk;
   __shared__ long long s_min, s_max;
+  __shared__ int64_t s_rp[kRowsPerGrab + 1];
+  __shared__ int64_t s_rpc[kRowsPerGrab];
   __shared__ int64_t s_bs[kABatch];
   __shared__ int s_len[kABatch];
+  __shared__ int2 s_se[kABatch];                    // flat path: [first, last+1) product number of each A entry
+  __shared__ unsigned char s_ent[kStageCap / 32];  // flat path: A entry that owns product 32*k
   __shared__ T s_av[NUMERIC ? kABatch : 1];
+  __shared__ unsigned char tflag[kSpThreads];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NWARP = kSpThreads / 32;
-  for (int i = tid; i < WW + NSW; i += kSpThreads) bitmap[i] = 0;  // summary is contiguous after bitmap
-  __syncthreads();
+  for (uint32_t q = tid; q < WW; q += kSpThreads) bitmap[q] = 0;
+  tflag[tid] = 0;
 
-  const T* va = (const T*)p.val_a;
-  const T* vb = (const T*)p.val_b;
+  const T* va = reinterpret_cast<const T*>(p.val_a);
+  const T* vb = reinterpret_cast<const T*>(p.val_b);
   const int64_t W = p.window_bits;
   const bool multi_window = p.N > W;
+  const bool has_val = NUMERIC && p.val_c != nullptr;
+  T* val_c = reinterpret_cast<T*>(p.val_c);
+
+  // next row's A-row metadata, prefetched into registers while the current row is processed
+  bool pf_valid = false;
+  int64_t pf_bs = 0;
+  int pf_len = 0;
+  T pf_av = (T)1;
 
   while (true) {
-    if (tid == 0) s_row = atomicAdd(p.counter, 1u);
     __syncthreads();
-    const int64_t i = s_row;
-    const int64_t a_s = p.rowptr_a[i < p.M ? i : 0], a_e = p.rowptr_a[i < p.M ? i + 1 : 0];
+    if (tid == 0) s_chunk = atomicAdd(p.counter, (unsigned int)kRowsPerGrab);
     __syncthreads();
-    if (i >= p.M) break;
-    int64_t win_lo = 0, win_hi = 0;  // window index range [win_lo, win_hi]
-    if (multi_window) {
-      // B rows are column-sorted (SparseStorage invariant): first/last entry bound the row's columns
-      if (tid == 0) { s_min = 0x7fffffffffffffffLL; s_max = -1; }
-      __syncthreads();
-      long long mn = 0x7fffffffffffffffLL, mx = -1;
-      for (int64_t a = a_s + tid; a < a_e; a += kSpThreads) {
-        const int64_t k = p.col_a[a];
-        const int64_t bs = p.rowptr_b[k], be = p.rowptr_b[k + 1];
-        if (be > bs) {
-          mn = min(mn, (long long)p.col_b[bs]);
-          mx = max(mx, (long long)p.col_b[be - 1]);
+    const int64_t r0 = s_chunk;
+    if (r0 >= p.M) break;
+    const int nr = (int)min((int64_t)kRowsPerGrab, p.M - r0);
+    if (tid <= nr) s_rp[tid] = p.rowptr_a[r0 + tid];
+    if (NUMERIC && tid < nr) s_rpc[tid] = p.rowptr_c[r0 + tid];
+    __syncthreads();
+    pf_valid = false;
+
+    for (int j = 0; j < nr; j++) {
+      const int64_t i = r0 + j;
+      const int64_t a_s = s_rp[j], a_e = s_rp[j + 1];
+      const int64_t n_a = a_e - a_s;
+      if (n_a <= 0) { pf_valid = false; continue; }  // counts[i] stays 0 (pre-zeroed); no output
+      const int na0 = (int)min(n_a, (int64_t)kABatch);
+
+      // ---- stage the (first batch of the) A-row metadata: start/length of each B row, a_ik; number the products ----
+      int64_t bs = 0;
+      int len = 0;
+      T av = (T)1;
+      if (pf_valid) { bs = pf_bs; len = pf_len; av = pf_av; }
+      else if (tid < na0) {
+        const int64_t k = p.col_a[a_s + tid];
+        bs = p.rowptr_b[k];
+        len = (int)(p.rowptr_b[k + 1] - bs);
+        if (NUMERIC && va) av = va[a_s + tid];
+      }
+      if (tid >= na0) len = 0;
+      if (tid < na0) {
+        s_bs[tid] = bs;
+        s_len[tid] = len;
+        if (NUMERIC) s_av[tid] = av;
+      }
+      const int len_c = min(len, kStageCap + 1);  // keeps the sum in range; any clamped length disables the flat path
+      int P;
+      const int excl = sp_block_scan(len_c, s_warp, P);
+      if (tid < na0) {
+        s_se[tid] = make_int2(excl, excl + len_c);
+        // the 32-aligned product numbers inside [excl, excl + len): this entry is where their chunk starts
+        if (P <= kStageCap)
+          for (int k = (excl + 31) >> 5; (k << 5) < excl + len_c; k++) s_ent[k] = (unsigned char)tid;
+      }
+      pf_valid = false;
+
+      // ---- issue the first load of the next row's metadata (completed mid-row) ----
+      bool do_pf = false;
+      int64_t nk = -1, nx_s = 0;
+      if (j + 1 < nr) {
+        nx_s = s_rp[j + 1];
+        const int64_t nn = s_rp[j + 2] - nx_s;
+        if (nn > 0 && nn <= kABatch) {
+          do_pf = true;
+          if (tid < nn) nk = p.col_a[nx_s + tid];
         }
       }
-      if (mx >= 0) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); }
-      __syncthreads();
-      if (s_max < 0) { win_lo = 1; win_hi = 0; }
-      else { win_lo = s_min / W; win_hi = s_max / W; }
-      __syncthreads();
-    }
-    const bool single_batch = (a_e - a_s) <= kABatch;
-    int64_t done = 0;  // nnz of this row emitted by previous windows
-    const int64_t out0 = NUMERIC ? p.rowptr_c[i] : 0;
-    bool staged = false;
+#define SP_PF_STAGE2()                                             \
+  if (do_pf) {                                                     \
+    if (nk >= 0) {                                                 \
+      pf_bs = p.rowptr_b[nk];                                      \
+      pf_len = (int)(p.rowptr_b[nk + 1] - pf_bs);                  \
+      pf_av = (NUMERIC && va) ? va[nx_s + tid] : (T)1;             \
+    }                                                              \
+    pf_valid = true;                                               \
+  }
+      __syncthreads();  // s_bs / s_len / s_se / s_ent / s_av visible
 
-    for (int64_t win = win_lo; win <= win_hi; win++) {
-      const int64_t wlo = win * W, whi = wlo + W;
-      // ---- mark ----
-      for (int64_t ab = a_s; ab < a_e; ab += kABatch) {
-        const int na = (int)min((int64_t)kABatch, a_e - ab);
-        if (!(single_batch && staged)) {
-          if (tid < na) {
-            const int64_t k = p.col_a[ab + tid];
-            const int64_t bs = p.rowptr_b[k];
-            s_bs[tid] = bs;
-            s_len[tid] = (int)(p.rowptr_b[k + 1] - bs);
-            if (NUMERIC) s_av[tid] = va ? va[ab + tid] : (T)1;
-          }
-          __syncthreads();
-          staged = true;
-        }
-        for (int e = warp; e < na; e += NWARP) {
-          const int64_t bs = s_bs[e];
-          const int len = s_len[e];
-          for (int f = lane; f < len; f += 32) {
-            const int64_t c = p.col_b[bs + f];
-            if (c >= wlo && c < whi) {
-              const uint32_t cc = (uint32_t)(c - wlo);
-              const uint32_t old = atomicOr(&bitmap[cc >> 5], 1u << (cc & 31));
-              if (old == 0) atomicOr(&summary[cc >> 10], 1u << ((cc >> 5) & 31));
+      const bool flat = !multi_window && n_a <= kABatch && P <= kStageCap;
+      if (flat) {
+        // ================= flat row: products 0..P-1 dealt to the threads, kept in registers =================
+        // product q lives in chunk q >> 5; chunk c is handled by warp c % 8 as its slot c / 8 (balanced to one chunk)
+        uint32_t cc[kFlatU];  // window-relative column (18 bit) | rank << 18 once known; ~0 = no product
+        T pv[kFlatU];
+#pragma unroll
+        for (int u = 0; u < kFlatU; u++) {
+          cc[u] = 0xffffffffu;
+          pv[u] = (T)0;
+          const int q = ((warp + kSpWarps * u) << 5) + lane;
+          if (((warp + kSpWarps * u) << 5) < P) {   // warp-uniform
+            if (q < P) {
+              int e = s_ent[warp + kSpWarps * u];
+              int2 se = s_se[e];
+              while (q >= se.y) se = s_se[++e];
+              const int64_t idx = s_bs[e] + (q - se.x);
+              cc[u] = (uint32_t)__ldg(p.col_b + idx);
+              if (has_val) pv[u] = s_av[e] * (vb ? __ldg(vb + idx) : (T)1);
             }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kFlatU; u++)
+          if (cc[u] != 0xffffffffu) sp_mark(bitmap, cc[u]);
+        __syncthreads();
+        SP_PF_STAGE2();
+#pragma unroll
+        for (int u = 0; u < kFlatU; u++)
+          if (cc[u] != 0xffffffffu) sp_verify(bitmap, cc[u]);
+        __syncthreads();
+        if (!NUMERIC) {
+          int cnt = (uint32_t)tid < NCH ? sp_count_clear_chunk(bitmap, lw) : 0;
+#pragma unroll
+          for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+          if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + i), (unsigned long long)cnt);
+          continue;  // the next row's staging barriers order the clears before its marks
+        }
+        const int wc = sp_scan<true>(bitmap, pre4, tbase, tflag, lw, NCH, s_warp);
+        const int64_t ob = s_rpc[j];
+        __syncthreads();
+        // rank; every product writes (its id, its column) into the slot: the last writer owns the slot
+#pragma unroll
+        for (int u = 0; u < kFlatU; u++) {
+          if (cc[u] != 0xffffffffu) {
+            const uint32_t r = sp_rank<true>(bitmap, pre4, tbase, lw, cc[u]);
+            const uint32_t q = (uint32_t)(((warp + kSpWarps * u) << 5) + lane);
+            scol[r] = (q << kMaxWindowLog2) | cc[u];
+            cc[u] |= r << kMaxWindowLog2;
           }
         }
         __syncthreads();
+        if (has_val) {
+          uint32_t dmask = 0;
+#pragma unroll
+          for (int u = 0; u < kFlatU; u++) {
+            if (cc[u] != 0xffffffffu) {
+              const uint32_t r = cc[u] >> kMaxWindowLog2;
+              const uint32_t q = (uint32_t)(((warp + kSpWarps * u) << 5) + lane);
+              if ((scol[r] >> kMaxWindowLog2) == q) acc[r] = pv[u];
+              else dmask |= 1u << u;
+            }
+          }
+          if (__syncthreads_or(dmask != 0)) {
+#pragma unroll
+            for (int u = 0; u < kFlatU; u++)
+              if (dmask & (1u << u)) atomicAdd(&acc[cc[u] >> kMaxWindowLog2], pv[u]);
+            __syncthreads();
+          }
+        }
+        for (int q = tid; q < wc; q += kSpThreads) {
+          __stcs(p.col_c + ob + q, (int64_t)(scol[q] & (uint32_t)(kMaxWindowBits - 1)));
+          if (p.row_c) __stcs(p.row_c + ob + q, i);
+          if (has_val) __stcs(val_c + ob + q, acc[q]);
+        }
+#pragma unroll
+        for (int u = 0; u < kFlatU; u++)
+          if (cc[u] != 0xffffffffu) bitmap[sp_phys((cc[u] & (uint32_t)(kMaxWindowBits - 1)) >> 5)] = 0;
+        continue;  // the next row's staging barriers order the clears / staging reads before its writes
       }
 
-      if (!NUMERIC) {
-        int cnt = 0;
-        for (int sw = tid; sw < NSW; sw += kSpThreads) {
-          uint32_t m = summary[sw];
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int w = (sw << 5) + b;
-            cnt += __popc(bitmap[w]);
-            bitmap[w] = 0;
-          }
-          summary[sw] = 0;
-        }
-        int total;
-        block_exclusive_scan(cnt, s_warp, total);
-        done += total;
-      } else {
-        // ---- rank: prefix of popcounts over touched words ----
-        const int spt = (NSW + kSpThreads - 1) / kSpThreads;
-        const int sw0 = tid * spt, sw1 = min(NSW, sw0 + spt);
-        int mine = 0;
-        for (int sw = sw0; sw < sw1; sw++) {
-          uint32_t m = summary[sw];
-          int run = 0;
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int w = (sw << 5) + b;
-            pre16[w] = (uint16_t)run;
-            run += __popc(bitmap[w]);
-          }
-          base[sw] = run;
-          mine += run;
-        }
-        int wc;
-        int off = block_exclusive_scan(mine, s_warp, wc);
-        for (int sw = sw0; sw < sw1; sw++) {
-          const int t = base[sw];
-          base[sw] = off;
-          off += t;
-        }
-        const bool use_smem_acc = p.val_c != nullptr && wc <= p.acc_cap;
-        const int64_t obase = out0 + done;
-        if (p.val_c) {
-          if (use_smem_acc) for (int q = tid; q < wc; q += kSpThreads) acc[q] = (T)0;
-          else for (int q = tid; q < wc; q += kSpThreads) ((T*)p.val_c)[obase + q] = (T)0;
-        }
+      // ================= general row: products re-walked per pass, window by window =================
+      int64_t win_lo = 0, win_hi = 0;  // window index range [win_lo, win_hi]
+      if (multi_window) {
+        // B rows are column-sorted (SparseStorage invariant): first/last entry bound the row's columns
+        if (tid == 0) { s_min = 0x7fffffffffffffffLL; s_max = -1; }
         __syncthreads();
-        // ---- emit columns (already sorted) ----
-        for (int sw = tid; sw < NSW; sw += kSpThreads) {
-          uint32_t m = summary[sw];
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int w = (sw << 5) + b;
-            uint32_t bits = bitmap[w];
-            int64_t pos = obase + base[sw] + pre16[w];
-            while (bits) {
-              const int bb = __ffs(bits) - 1;
-              bits &= bits - 1;
-              p.col_c[pos] = wlo + ((int64_t)w << 5) + bb;
-              if (p.row_c) p.row_c[pos] = i;
-              pos++;
-            }
+        long long mn = 0x7fffffffffffffffLL, mx = -1;
+        for (int64_t a = a_s + tid; a < a_e; a += kSpThreads) {
+          const int64_t k = p.col_a[a];
+          const int64_t kb = p.rowptr_b[k], ke = p.rowptr_b[k + 1];
+          if (ke > kb) {
+            mn = min(mn, (long long)p.col_b[kb]);
+            mx = max(mx, (long long)p.col_b[ke - 1]);
           }
         }
-        // ---- accumulate values at their rank ----
-        if (p.val_c) {
-          for (int64_t ab = a_s; ab < a_e; ab += kABatch) {
-            const int na = (int)min((int64_t)kABatch, a_e - ab);
-            if (!single_batch) {
-              __syncthreads();
-              if (tid < na) {
-                const int64_t k = p.col_a[ab + tid];
-                const int64_t bs = p.rowptr_b[k];
-                s_bs[tid] = bs;
-                s_len[tid] = (int)(p.rowptr_b[k + 1] - bs);
-                s_av[tid] = va ? va[ab + tid] : (T)1;
-              }
-              __syncthreads();
-            }
-            for (int e = warp; e < na; e += NWARP) {
-              const int64_t bs = s_bs[e];
-              const int len = s_len[e];
-              const T av = s_av[e];
-              for (int f = lane; f < len; f += 32) {
-                const int64_t c = p.col_b[bs + f];
-                if (c >= wlo && c < whi) {
-                  const uint32_t cc = (uint32_t)(c - wlo);
-                  const uint32_t w = cc >> 5;
-                  const int rank = base[w >> 5] + pre16[w] + __popc(bitmap[w] & ((1u << (cc & 31)) - 1u));
-                  const T pv = av * (vb ? vb[bs + f] : (T)1);
-                  if (use_smem_acc) atomicAdd(&acc[rank], pv);
-                  else atomicAdd(((T*)p.val_c) + obase + rank, pv);
-                }
-              }
-            }
+        if (mx >= 0) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); }
+        __syncthreads();
+        if (s_max < 0) { win_lo = 1; win_hi = 0; }
+        else { win_lo = s_min / W; win_hi = s_max / W; }
+        __syncthreads();
+      }
+      const bool single_batch = n_a <= kABatch;
+      int64_t done = 0;  // nnz of this row emitted by previous windows
+      const int64_t out0 = NUMERIC ? s_rpc[j] : 0;
+      int cnt = 0;       // symbolic: columns this thread was first on
+
+      // walk every product of the row that falls into [wlo, whi); BODY sees c (column), c0 (window-relative),
+      // e (A entry in the staged batch), ebs + f (index into B)
+#define SP_WALK(BODY)                                                              \
+  for (int64_t ab = a_s; ab < a_e; ab += kABatch) {                                \
+    const int na = (int)min((int64_t)kABatch, a_e - ab);                           \
+    if (!single_batch) {                                                           \
+      __syncthreads();                                                             \
+      if (tid < na) {                                                              \
+        const int64_t k = p.col_a[ab + tid];                                       \
+        const int64_t kb = p.rowptr_b[k];                                          \
+        s_bs[tid] = kb;                                                            \
+        s_len[tid] = (int)(p.rowptr_b[k + 1] - kb);                                \
+        if (NUMERIC) s_av[tid] = va ? va[ab + tid] : (T)1;                         \
+      }                                                                            \
+      __syncthreads();                                                             \
+    }                                                                              \
+    for (int e = warp; e < na; e += kSpWarps) {                                    \
+      const int64_t ebs = s_bs[e];                                                 \
+      const int elen = s_len[e];                                                   \
+      for (int f = lane; f < elen; f += 32) {                                      \
+        const int64_t c = __ldg(p.col_b + ebs + f);                                \
+        if (c >= wlo && c < whi) {                                                 \
+          const uint32_t c0 = (uint32_t)(c - wlo);                                 \
+          BODY                                                                     \
+        }                                                                          \
+      }                                                                            \
+    }                                                                              \
+  }
+
+      for (int64_t win = win_lo; win <= win_hi; win++) {
+        const int64_t wlo = win * W, whi = wlo + W;
+        // ---- mark ----
+        SP_WALK({
+          const uint32_t bit = 1u << (c0 & 31u);
+          const uint32_t old = atomicOr(&bitmap[sp_phys(c0 >> 5)], bit);
+          if (!NUMERIC && !(old & bit)) cnt++;
+          tflag[c0 >> (5 + lw)] = 1;
+        })
+        __syncthreads();
+
+        if (!NUMERIC) {
+          // ---- clear touched chunks ----
+          if ((uint32_t)tid < NCH && tflag[tid]) {
+            sp_count_clear_chunk(bitmap, lw);
+            tflag[tid] = 0;
           }
-          __syncthreads();
-          if (use_smem_acc) for (int q = tid; q < wc; q += kSpThreads) ((T*)p.val_c)[obase + q] = acc[q];
         } else {
+          const int wc = sp_scan<false>(bitmap, pre4, tbase, tflag, lw, NCH, s_warp);
+          const int64_t ob = out0 + done;
+          const bool staged = wc <= kStageCap;  // columns staged in shared memory -> coalesced stores
+          if (has_val)
+            for (int q = tid; q < wc; q += kSpThreads) val_c[ob + q] = (T)0;
           __syncthreads();
-        }
-        // ---- clear touched words ----
-        for (int sw = tid; sw < NSW; sw += kSpThreads) {
-          uint32_t m = summary[sw];
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            bitmap[(sw << 5) + b] = 0;
+          // ---- rank every product: column (same-value races are benign), value via L2 atomics ----
+          SP_WALK({
+            const uint32_t r = sp_rank<false>(bitmap, pre4, tbase, lw, c0);
+            if (staged) {
+              scol[r] = c0;
+            } else {
+              p.col_c[ob + r] = c;
+              if (p.row_c) p.row_c[ob + r] = i;
+            }
+            if (has_val) atomicAdd(val_c + ob + r, s_av[e] * (vb ? __ldg(vb + ebs + f) : (T)1));
+          })
+          __syncthreads();
+          if (staged) {
+            for (int q = tid; q < wc; q += kSpThreads) {
+              __stcs(p.col_c + ob + q, wlo + (int64_t)scol[q]);
+              if (p.row_c) __stcs(p.row_c + ob + q, i);
+            }
           }
-          summary[sw] = 0;
+          // ---- clear touched chunks ----
+          if ((uint32_t)tid < NCH && tflag[tid]) {
+            sp_count_clear_chunk(bitmap, lw);
+            tflag[tid] = 0;
+          }
+          done += wc;
         }
-        done += wc;
+        __syncthreads();
       }
-      __syncthreads();
+#undef SP_WALK
+      if (!NUMERIC) {
+#pragma unroll
+        for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + i), (unsigned long long)cnt);
+      }
+      SP_PF_STAGE2();
+#undef SP_PF_STAGE2
     }
-    if (!NUMERIC && tid == 0) p.counts[i] = done;
   }
 }
 
-__global__ void sp_finish_kernel(int64_t* rowptr_c, int64_t M, int64_t* nnz_dev) {
-  rowptr_c[0] = 0;
-  (void)M;
-  (void)nnz_dev;
-}
 __global__ void sp_copy_last_kernel(const int64_t* rowptr_c, int64_t M, int64_t* nnz_dev) { *nnz_dev = rowptr_c[M]; }
 
 static int window_bits_for(int64_t N) {
@@ -296,10 +502,17 @@ static int window_bits_for(int64_t N) {
   while (w < N && w < kMaxWindowBits) w <<= 1;
   return (int)w;
 }
-static size_t sp_smem_bytes(int window_bits, bool numeric, size_t elem, int acc_cap) {
-  const size_t WW = (size_t)window_bits >> 5, NSW = WW >> 5;
-  size_t b = WW * 4 + NSW * 4;
-  if (numeric) b += NSW * 4 + WW * 2 + (size_t)acc_cap * elem;
+static int log2_wpt_for(int window_bits) {
+  int wpt = (window_bits >> 5) / kSpThreads;  // words per thread when every thread owns one chunk
+  if (wpt < 4) wpt = 4;
+  int lw = 2;
+  while ((1 << lw) < wpt) lw++;
+  return lw;  // 2..5 for windows up to 2^18
+}
+static size_t sp_smem_bytes(int window_bits, bool numeric, size_t elem) {
+  const size_t WW = (size_t)window_bits >> 5;
+  size_t b = WW * 4;
+  if (numeric) b += WW / 4 * 2 + (size_t)kStageCap * 4 + (size_t)kStageCap * elem;  // acc also hosts tbase (1 KB)
   return b;
 }
 
@@ -318,7 +531,7 @@ static SpLayout sp_layout(int64_t M) {
 }
 
 template <bool NUMERIC, typename T> static int sp_launch(const SpParams& p, cudaStream_t st) {
-  const size_t smem = sp_smem_bytes(p.window_bits, NUMERIC, sizeof(T), p.acc_cap);
+  const size_t smem = sp_smem_bytes(p.window_bits, NUMERIC, sizeof(T));
   auto* k = spspmm_kernel<NUMERIC, T>;
   TSB_CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -327,7 +540,8 @@ template <bool NUMERIC, typename T> static int sp_launch(const SpParams& p, cuda
   int dev = 0, sms = kNumSMs;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int64_t grid = (int64_t)per_sm * sms;
-  if (grid > p.M) grid = p.M;
+  const int64_t grabs = (p.M + kRowsPerGrab - 1) / kRowsPerGrab;
+  if (grid > grabs) grid = grabs;
   if (grid < 1) grid = 1;
   k<<<(int)grid, kSpThreads, smem, st>>>(p);
   TSB_LAUNCH_CHECK();
@@ -368,7 +582,7 @@ extern "C" int tsb200_spspmm_symbolic(const int64_t* rowptr_a, const int64_t* co
   p.counts = rowptr_c + 1; p.rowptr_c = nullptr; p.row_c = nullptr; p.col_c = nullptr; p.val_c = nullptr;
   p.counter = (unsigned int*)(ws + L.scalars);
   p.window_bits = window_bits_for(N);
-  p.acc_cap = 0;
+  p.log2_wpt = log2_wpt_for(p.window_bits);
   int rc = sp_launch<false, float>(p, st);
   if (rc) return rc;
   size_t tb = L.cub_bytes;
@@ -401,12 +615,7 @@ extern "C" int tsb200_spspmm_numeric(const int64_t* rowptr_a, const int64_t* col
   p.counts = nullptr; p.rowptr_c = rowptr_c; p.row_c = row_c; p.col_c = col_c; p.val_c = val_c;
   p.counter = (unsigned int*)(ws + L.scalars);
   p.window_bits = window_bits_for(N);
-  {
-    // 0 = accumulate with L2 atomics straight into val_c (measured faster than a 16 KB shared accumulator:
-    // 4 instead of 3 resident CTAs/SM and two fewer passes); the knob stays for experiments
-    static const int acc = getenv("TSB200_SPSPMM_ACC") ? atoi(getenv("TSB200_SPSPMM_ACC")) : 0;
-    p.acc_cap = val_c ? acc : 0;
-  }
+  p.log2_wpt = log2_wpt_for(p.window_bits);
   if (val_c && dtype == TSB200_F64) return sp_launch<true, double>(p, st);
   return sp_launch<true, float>(p, st);
 }

@@ -62,8 +62,14 @@ def test_orthonormal_rows(dtype):
 @pytest.mark.parametrize("M,Kd,N,da,db,dtype", [
     (200, 150, 180, 6, 5, torch.float32),
     (64, 3000, 70000, 12, 40, torch.float32),     # N > 65536
-    (50, 400, 700_000, 10, 300, torch.float64),   # N > one 2^19-column window: multi-window path
-    (30, 40, 5000, 30, 1000, torch.float32),      # rows wider than the 4096-entry shared accumulator
+    (50, 400, 700_000, 10, 300, torch.float64),   # N > one 2^18-column window: multi-window path
+    (30, 40, 5000, 30, 1000, torch.float32),      # rows wider than the 1024-entry shared staging area
+    (300, 64, 96, 28, 28, torch.float32),         # simple-row path, >= 3 products per output column (duplicates)
+    (300, 64, 96, 28, 28, torch.float64),
+    (257, 500, 262_144, 30, 30, torch.float32),   # simple and general rows mixed (Poisson(30) straddles 32), full window
+    (40, 3000, 20_000, 400, 3, torch.float32),    # A rows longer than one 256-entry batch, short B rows
+    (64, 200, 1500, 20, 60, torch.float32),       # B rows longer than 32 (general path), output staged in smem
+    (37, 50, 33, 5, 4, torch.float64),            # tiny window (1024 bits, 4-word scan chunks)
 ])
 def test_random_vs_oracle(oracle, M, Kd, N, da, db, dtype):
     _, rpa, ca = random_csr(M, Kd, da, seed=1, empty_rows=(0,))
