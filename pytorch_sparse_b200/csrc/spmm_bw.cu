@@ -546,20 +546,21 @@ extern "C" int tsb200_spmm_minmax_bw(const int64_t* col, const void* value, cons
   return dispatch_float_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     using A = typename std::conditional<std::is_same<T, double>::value, double, float>::type;
-    // feature slice: largest power of two whose mat / grad_mat columns fit the L2 budget; never narrower than one
-    // 128-byte L2 line (L2 capacity is counted in LINES: a slice using one 32-byte sector of each line would
-    // occupy four times its size)
+    // feature slice (measured at C3, scripts/sweep_minmax_bw.py -> profiles/r01_minmax_bw_sweep.txt): whole rows while
+    // mat + grad_mat fit L2; otherwise 256-byte slices of a row when both gradients are wanted (2.47 -> 1.95 ms),
+    // 128-byte slices (one L2 line; narrower slices waste line capacity and are slower) for a single gradient
+    // (grad_mat only: 1.62 -> 1.16 ms)
     int full = 0;
-    while (((int64_t)1 << full) < K) full++;  // whole rows when everything fits
-    const int min_lsl = sizeof(T) >= 8 ? 4 : (sizeof(T) >= 4 ? 5 : 6);
+    while (((int64_t)1 << full) < K) full++;
     int lsl = full;
-    const double per_feature = (double)B * (double)N * (double)sizeof(A);
-    while (lsl > min_lsl && per_feature * (double)((int64_t)1 << lsl) > 40.0 * 1024 * 1024) lsl--;
-    // with both gradients requested the mat slice (read) and the grad_mat slice (atomics) would have to share L2:
-    // run two passes, each with one resident slice, unless a whole-row walk fits anyway
-    bool split = grad_value && grad_mat && lsl < full;
+    const double resident = (double)B * (double)N * (double)K * (double)(sizeof(T) + sizeof(A));
+    if (resident > 64.0 * 1024 * 1024) {
+      const int slice_bytes = (grad_value && grad_mat) ? 256 : 128;
+      lsl = 0;
+      while ((size_t)(2u << lsl) * sizeof(T) <= (size_t)slice_bytes) lsl++;
+      if (lsl > full) lsl = full;
+    }
     if (const char* ev = getenv("TSB200_MMBW_LSL")) { lsl = atoi(ev); if (lsl > full) lsl = full; if (lsl < 0) lsl = 0; }
-    if (const char* ev = getenv("TSB200_MMBW_SPLIT")) split = atoi(ev) != 0 && grad_value && grad_mat;
     // persistent grid: every CTA resident, so all of them walk the slices in step
     int per_sm = 8;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)minmax_bw_kernel<T, A>, 256, 0);
@@ -567,16 +568,8 @@ extern "C" int tsb200_spmm_minmax_bw(const int64_t* col, const void* value, cons
     int64_t blocks = ((B * M << lsl) + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * per_sm;
     if (blocks > cap) blocks = cap;
-    if (split) {
-      minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
-                                                         arg_out, (A*)nullptr, (A*)grad_mat, B, M, N, K, E, lsl);
-      TSB_LAUNCH_CHECK();
-      minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
-                                                         arg_out, (A*)grad_value, (A*)nullptr, B, M, N, K, E, lsl);
-    } else {
-      minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
-                                                         arg_out, (A*)grad_value, (A*)grad_mat, B, M, N, K, E, lsl);
-    }
+    minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
+                                                       arg_out, (A*)grad_value, (A*)grad_mat, B, M, N, K, E, lsl);
     TSB_LAUNCH_CHECK();
     return 0;
   });

@@ -188,7 +188,7 @@ __device__ __forceinline__ int sp_count_clear_chunk(uint32_t* bitmap, int lw) {
 }
 
 template <bool NUMERIC, typename T>
-__global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 4) spspmm_kernel(const SpParams p) {
+__global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : (NUMERIC ? 4 : 5)) spspmm_kernel(const SpParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t WW = (uint32_t)p.window_bits >> 5;   // bitmap words (>= 32)
   const int lw = p.log2_wpt;

@@ -1,4 +1,4 @@
-"""Sweep the feature-slice width / pass split of the fused min/max backward at BASELINE configs[2] scale
+"""Sweep the feature-slice width of the fused min/max backward at BASELINE configs[2] scale
 (each configuration in a fresh process: the knobs are read from the environment by libtsb200)."""
 import json, os, subprocess, sys
 from pathlib import Path
@@ -33,10 +33,10 @@ print(json.dumps(dict(lsl=os.environ.get("TSB200_MMBW_LSL", "auto"), split=os.en
                       both_ms=both, only_mat_ms=only_mat, only_val_ms=only_val, zero_fill_ms=zero)), flush=True)
 ''' % (str(ROOT), str(ROOT))
 
-configs = [("auto", "auto")] + [(str(l), s) for l in (8, 6, 5, 4) for s in ("0", "1")]
+configs = [("auto", "auto")] + [(str(l), "0") for l in (8, 7, 6, 5, 4)]
 for lsl, split in configs:
     env = dict(os.environ)
     if lsl != "auto":
-        env["TSB200_MMBW_LSL"] = lsl; env["TSB200_MMBW_SPLIT"] = split
+        env["TSB200_MMBW_LSL"] = lsl
     r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
     print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "ERR " + r.stderr[-400:], flush=True)
