@@ -230,9 +230,51 @@ def main():
                 "narrow1": dict(row=n1.storage.row(), col=n1.storage.col(), value=n1.storage.value(), sizes=n1.sparse_sizes())},
                GOLD / "next_rows.pt")
 
+    gen_next_rows2(ts, meta)
+
     sizes = {p.name: p.stat().st_size for p in sorted(GOLD.glob("*.pt"))}
     print("wrote", sizes, "total", sum(sizes.values()))
 
 
+def gen_next_rows2(ts, meta):
+    """to_symmetric (tensor.py:404-438), index_select / index_select_nnz
+    (index_select.py:9-99) run through the unmodified reference."""
+    from torch_sparse import SparseTensor
+    g = torch.Generator().manual_seed(71)
+    out = {"meta": meta, "cases": {}}
+    for name, (M, N, deg) in {"rect": (37, 29, 4), "square": (33, 33, 5)}.items():
+        r, c = random_structure(M, N, deg, seed=72 + M, empty_rows=(0, 5))
+        v = torch.randn(r.numel(), generator=g, dtype=torch.float64)
+        v2 = torch.randn(r.numel(), 2, generator=g, dtype=torch.float64)
+        A = SparseTensor(row=r, col=c, value=v, sparse_sizes=(M, N))
+        A2 = SparseTensor(row=r, col=c, value=v2, sparse_sizes=(M, N))
+        A0 = SparseTensor(row=r, col=c, sparse_sizes=(M, N))
+        idx0 = torch.randint(M, (25,), generator=g)          # unsorted, with repeats
+        idx1 = torch.randint(N, (19,), generator=g)
+        idxe = torch.randperm(r.numel(), generator=g)[: r.numel() // 2].sort().values
+        case = {"in": dict(row=r, col=c, v=v, v2=v2, M=M, N=N, idx0=idx0, idx1=idx1, idxe=idxe)}
+        for tag, T in (("v", A), ("v2", A2), ("nv", A0)):
+            s0 = T.index_select(0, idx0)
+            s1 = T.index_select(1, idx1)
+            case[f"sel0_{tag}"] = dict(rowptr=s0.storage.rowptr(), row=s0.storage.row(), col=s0.storage.col(),
+                                       value=s0.storage.value(), sizes=s0.sparse_sizes())
+            case[f"sel1_{tag}"] = dict(row=s1.storage.row(), col=s1.storage.col(), value=s1.storage.value(),
+                                       colptr=s1.storage.colptr(), sizes=s1.sparse_sizes())
+            for lay in ("coo", "csc"):
+                sn = T.index_select_nnz(idxe, lay)
+                case[f"selnnz_{lay}_{tag}"] = dict(row=sn.storage.row(), col=sn.storage.col(), value=sn.storage.value())
+            for red in ("sum", "mean", "min", "max"):
+                if tag == "nv" and red != "sum":
+                    continue
+                sy = T.to_symmetric(red)
+                case[f"sym_{red}_{tag}"] = dict(row=sy.storage.row(), col=sy.storage.col(), value=sy.storage.value(),
+                                                sizes=sy.sparse_sizes())
+        out["cases"][name] = case
+    torch.save(out, GOLD / "next_rows2.pt")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "next_rows2":
+        gen_next_rows2(import_reference(), {"reference": "rusty1s/pytorch_sparse 0.6.18 @ 91feaa5e", "torch": torch.__version__})
+    else:
+        main()

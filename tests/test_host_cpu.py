@@ -202,3 +202,27 @@ def test_pinned_output_pool_never_aliases_live_results():
     del view
     d = ops._pinned_empty((4, 8), torch.bfloat16, pin=False)
     assert d.data_ptr() == pa          # now it may be reused
+
+
+def test_index_select_host_bookkeeping_matches_reference():
+    """index_select / index_select_nnz (torch_sparse/index_select.py:9-99) are pure index bookkeeping: on CPU
+    tensors (storage construction path, no arithmetic) they reproduce the unmodified reference's outputs
+    (tests/golden/next_rows2.pt) bit for bit."""
+    d = torch.load(Path(__file__).resolve().parent / "golden" / "next_rows2.pt", weights_only=False)
+    for name, case in d["cases"].items():
+        i = case["in"]
+        for tag in ("v", "v2", "nv"):
+            v = {"v": i["v"], "v2": i["v2"], "nv": None}[tag]
+            a = ts.SparseTensor(row=i["row"], col=i["col"], value=v, sparse_sizes=(i["M"], i["N"]))
+            s0, ref = a.index_select(0, i["idx0"]), case[f"sel0_{tag}"]
+            assert s0.sparse_sizes() == tuple(ref["sizes"])
+            assert torch.equal(s0.storage.rowptr(), ref["rowptr"]) and torch.equal(s0.storage.col(), ref["col"])
+            s1, ref = a.index_select(1, i["idx1"]), case[f"sel1_{tag}"]
+            assert torch.equal(s1.storage.row(), ref["row"]) and torch.equal(s1.storage.col(), ref["col"])
+            assert torch.equal(s1.storage.colptr(), ref["colptr"])
+            if v is not None:
+                assert torch.equal(s0.storage.value(), case[f"sel0_{tag}"]["value"])
+                assert torch.equal(s1.storage.value(), ref["value"])
+            for lay in ("coo", "csc"):
+                sn, ref = a.index_select_nnz(i["idxe"], lay), case[f"selnnz_{lay}_{tag}"]
+                assert torch.equal(sn.storage.row(), ref["row"]) and torch.equal(sn.storage.col(), ref["col"])

@@ -100,3 +100,65 @@ def test_mul_vs_reference_and_gcn_flow():
     dense = adj.to_dense()
     ref = (deg_r.pow(-0.5).view(-1, 1) * dense * deg_c.pow(-0.5).view(1, -1)) @ x
     assert torch.allclose(norm @ x, ref, atol=1e-10)
+
+
+# ---- §8(f) ranks 2 and 4: to_symmetric, index_select, index_select_nnz (golden: tests/golden/next_rows2.pt) ----
+D2 = torch.load(Path(__file__).resolve().parent / "golden" / "next_rows2.pt", weights_only=False)
+
+
+def _mk2(case, tag):
+    i = case["in"]
+    v = {"v": i["v"], "v2": i["v2"], "nv": None}[tag]
+    return ts.SparseTensor(row=i["row"].to(DEV), col=i["col"].to(DEV), value=None if v is None else v.to(DEV),
+                           sparse_sizes=(i["M"], i["N"]))
+
+
+def _same(got, ref, what):
+    if ref is None:
+        assert got is None, what
+    elif ref.dtype.is_floating_point:
+        assert torch.allclose(got.cpu(), ref, rtol=1e-12, atol=1e-12), what
+    else:
+        assert torch.equal(got.cpu(), ref), what
+
+
+@pytest.mark.parametrize("name", list(D2["cases"].keys()))
+@pytest.mark.parametrize("tag", ["v", "v2", "nv"])
+def test_index_select_vs_reference(name, tag):
+    case = D2["cases"][name]
+    i = case["in"]
+    a = _mk2(case, tag)
+    s0 = a.index_select(0, i["idx0"].to(DEV))
+    ref = case[f"sel0_{tag}"]
+    assert s0.sparse_sizes() == tuple(ref["sizes"])
+    for k in ("rowptr", "row", "col", "value"):
+        _same(getattr(s0.storage, k)(), ref[k], (name, tag, "sel0", k))   # indices bit-exact, values are gathered
+    s1 = a.index_select(1, i["idx1"].to(DEV))
+    ref = case[f"sel1_{tag}"]
+    assert s1.sparse_sizes() == tuple(ref["sizes"])
+    for k in ("row", "col", "value", "colptr"):
+        _same(getattr(s1.storage, k)(), ref[k], (name, tag, "sel1", k))
+    for lay in ("coo", "csc"):
+        sn = a.index_select_nnz(i["idxe"].to(DEV), lay)
+        ref = case[f"selnnz_{lay}_{tag}"]
+        for k in ("row", "col", "value"):
+            _same(getattr(sn.storage, k)(), ref[k], (name, tag, "selnnz", lay, k))
+    # the gathered rows feed SpMM directly (mini-batch path): rows of the product are the selected rows
+    if tag == "v":
+        x = torch.randn(i["N"], 16, device=DEV, dtype=torch.float64)
+        assert torch.allclose(s0 @ x, (a @ x)[i["idx0"].to(DEV)], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", list(D2["cases"].keys()))
+def test_to_symmetric_vs_reference(name):
+    case = D2["cases"][name]
+    for tag in ("v", "v2", "nv"):
+        a = _mk2(case, tag)
+        for red in ("sum", "mean", "min", "max"):
+            if f"sym_{red}_{tag}" not in case:
+                continue
+            ref = case[f"sym_{red}_{tag}"]
+            s = a.to_symmetric(red)
+            assert s.sparse_sizes() == tuple(ref["sizes"])
+            for k in ("row", "col", "value"):
+                _same(getattr(s.storage, k)(), ref[k], (name, tag, red, k))
