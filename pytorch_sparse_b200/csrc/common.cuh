@@ -130,6 +130,22 @@ __device__ __forceinline__ uint4 ldg128_hint(const void* p, uint64_t pol) {
                : "l"(p), "l"(pol));
   return r;
 }
+// scalar read-only loads with an L2 eviction-priority hint (operands that are re-read while a large output
+// streams through L2, e.g. B in SpSpMM)
+__device__ __forceinline__ uint64_t ldg64_hint(const void* p, uint64_t pol) {
+  uint64_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint32_t ldg32_hint(const void* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float ldg_hint(const float* p, uint64_t pol) { return __uint_as_float(ldg32_hint(p, pol)); }
+__device__ __forceinline__ double ldg_hint(const double* p, uint64_t pol) {
+  return __longlong_as_double((long long)ldg64_hint(p, pol));
+}
 __device__ __forceinline__ uint4 ldg128(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"

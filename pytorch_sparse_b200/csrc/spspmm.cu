@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
   const bool multi_window = p.N > W;
   const bool has_val = NUMERIC && p.val_c != nullptr;
   T* val_c = reinterpret_cast<T*>(p.val_c);
+  // B is re-read nnz(A)/Kd times while 20 bytes per output nonzero stream through L2: keep B's lines (evict_last)
+  const uint64_t pol_b = make_policy_evict_last();
 
   // next row's A-row metadata, prefetched into registers while the current row is processed
   bool pf_valid = false;
@@ -313,8 +315,8 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
               int2 se = s_se[e];
               while (q >= se.y) se = s_se[++e];
               const int64_t idx = s_bs[e] + (q - se.x);
-              cc[u] = (uint32_t)__ldg(p.col_b + idx);
-              if (has_val) pv[u] = s_av[e] * (vb ? __ldg(vb + idx) : (T)1);
+              cc[u] = (uint32_t)ldg64_hint(p.col_b + idx, pol_b);
+              if (has_val) pv[u] = s_av[e] * (vb ? ldg_hint(vb + idx, pol_b) : (T)1);
             }
           }
         }
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
       const int64_t ebs = s_bs[e];                                                 \
       const int elen = s_len[e];                                                   \
       for (int f = lane; f < elen; f += 32) {                                      \
-        const int64_t c = __ldg(p.col_b + ebs + f);                                \
+        const int64_t c = (int64_t)ldg64_hint(p.col_b + ebs + f, pol_b);           \
         if (c >= wlo && c < whi) {                                                 \
           const uint32_t c0 = (uint32_t)(c - wlo);                                 \
           BODY                                                                     \
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
               p.col_c[ob + r] = c;
               if (p.row_c) p.row_c[ob + r] = i;
             }
-            if (has_val) atomicAdd(val_c + ob + r, s_av[e] * (vb ? __ldg(vb + ebs + f) : (T)1));
+            if (has_val) atomicAdd(val_c + ob + r, s_av[e] * (vb ? ldg_hint(vb + ebs + f, pol_b) : (T)1));
           })
           __syncthreads();
           if (staged) {
