@@ -22,7 +22,7 @@ _ARG_LIKE = ("min", "max")
 def _views_for_backward(src: SparseTensor, value, other: Tensor, with_rowcount: bool) -> dict:
     """Cached views to pass along; anything not yet materialised stays None unless a gradient needs it."""
     st = src.storage
-    views = dict(row=st._row, rowcount=st._rowcount, colptr=st._colptr, csr2csc=st._csr2csc)
+    views = dict(row=st._row, rowcount=st._rowcount, colptr=st._colptr, csr2csc=st._csr2csc, row_csc=None)
     grad_value = value is not None and value.requires_grad
     grad_dense = other.requires_grad
     if grad_value or grad_dense:
@@ -30,6 +30,7 @@ def _views_for_backward(src: SparseTensor, value, other: Tensor, with_rowcount: 
     if grad_dense:                      # A^T @ grad_out runs on the CSC view
         views["csr2csc"] = st.csr2csc()
         views["colptr"] = st.colptr()
+        views["row_csc"] = st.row_csc()  # structure-only: gathered once per matrix instead of once per backward
         if with_rowcount:
             views["rowcount"] = st.rowcount()
     return views
@@ -44,8 +45,9 @@ def _run_spmm(src: SparseTensor, other: Tensor, reduce: str):
         return op(rowptr, col, value, other)
     v = _views_for_backward(src, value, other, with_rowcount=(reduce == "mean"))
     if reduce == "mean":
-        return ops.spmm_mean(v["row"], rowptr, col, value, v["rowcount"], v["colptr"], v["csr2csc"], other)
-    return ops.spmm_sum(v["row"], rowptr, col, value, v["colptr"], v["csr2csc"], other)
+        return ops.spmm_mean(v["row"], rowptr, col, value, v["rowcount"], v["colptr"], v["csr2csc"], other,
+                             row_csc=v["row_csc"])
+    return ops.spmm_sum(v["row"], rowptr, col, value, v["colptr"], v["csr2csc"], other, row_csc=v["row_csc"])
 
 
 def spmm_sum(src: SparseTensor, other: Tensor) -> Tensor:

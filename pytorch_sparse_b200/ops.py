@@ -446,7 +446,9 @@ def _assert_present(t: Optional[Tensor], name: str) -> None:
 
 class SPMMSum(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, row, rowptr, col, value, colptr, csr2csc, mat):
+    def forward(ctx, row, rowptr, col, value, colptr, csr2csc, mat, row_csc=None):
+        # row_csc (= row[csr2csc]) is an optional extra over the reference's signature: structure-only, so a
+        # caller that keeps it (SparseStorage.row_csc) saves one E-sized gather per backward (csrc/spmm.cpp:104)
         has_value = value is not None
         need_value = has_value and ctx.needs_input_grad[3]
         need_mat = ctx.needs_input_grad[6]
@@ -458,25 +460,27 @@ class SPMMSum(torch.autograd.Function):
             _assert_present(csr2csc, "csr2csc")
         out, _ = spmm_fw(rowptr, col, value, mat, "sum")
         ctx.has_value = has_value
-        ctx.save_for_backward(row, rowptr, col, value, colptr, csr2csc, mat)
+        ctx.save_for_backward(row, rowptr, col, value, colptr, csr2csc, mat, row_csc if need_mat else None)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        row, rowptr, col, value, colptr, csr2csc, mat = ctx.saved_tensors
+        row, rowptr, col, value, colptr, csr2csc, mat, row_csc = ctx.saved_tensors
         grad_value = grad_mat = None
         if ctx.has_value and ctx.needs_input_grad[3]:
             grad_value = spmm_value_bw(row, rowptr, col, mat, grad_out, "sum")
         if ctx.needs_input_grad[6]:
             # grad_mat = A^T @ grad_out as a CSR SpMM on the CSC view (csrc/spmm.cpp:100-108)
             v = value.index_select(0, csr2csc) if ctx.has_value else None
-            grad_mat, _ = spmm_fw(colptr, row.index_select(0, csr2csc), v, grad_out, "sum")
-        return None, None, None, grad_value, None, None, grad_mat
+            if row_csc is None:
+                row_csc = row.index_select(0, csr2csc)
+            grad_mat, _ = spmm_fw(colptr, row_csc, v, grad_out, "sum")
+        return None, None, None, grad_value, None, None, grad_mat, None
 
 
 class SPMMMean(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, row, rowptr, col, value, rowcount, colptr, csr2csc, mat):
+    def forward(ctx, row, rowptr, col, value, rowcount, colptr, csr2csc, mat, row_csc=None):
         has_value = value is not None
         if has_value and ctx.needs_input_grad[3]:
             _assert_present(row, "row")
@@ -487,22 +491,24 @@ class SPMMMean(torch.autograd.Function):
             _assert_present(csr2csc, "csr2csc")
         out, _ = spmm_fw(rowptr, col, value, mat, "mean")
         ctx.has_value = has_value
-        ctx.save_for_backward(row, rowptr, col, value, rowcount, colptr, csr2csc, mat)
+        ctx.save_for_backward(row, rowptr, col, value, rowcount, colptr, csr2csc, mat,
+                              row_csc if ctx.needs_input_grad[7] else None)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        row, rowptr, col, value, rowcount, colptr, csr2csc, mat = ctx.saved_tensors
+        row, rowptr, col, value, rowcount, colptr, csr2csc, mat, row_csc = ctx.saved_tensors
         grad_value = grad_mat = None
         if ctx.has_value and ctx.needs_input_grad[3]:
             grad_value = spmm_value_bw(row, rowptr, col, mat, grad_out, "mean")
         if ctx.needs_input_grad[7]:
             # per-nnz weight value/count(row) (or 1/count) in CSC order (csrc/spmm.cpp:166-177)
-            row_csc = row.index_select(0, csr2csc)
+            if row_csc is None:
+                row_csc = row.index_select(0, csr2csc)
             cnt = rowcount.index_select(0, row_csc).to(mat.dtype).clamp_(min=1)
             w = value.index_select(0, csr2csc).div(cnt) if ctx.has_value else cnt.reciprocal_()
             grad_mat, _ = spmm_fw(colptr, row_csc, w, grad_out, "sum")
-        return None, None, None, grad_value, None, None, None, grad_mat
+        return None, None, None, grad_value, None, None, None, grad_mat, None
 
 
 def _minmax_forward(ctx, reduce, rowptr, col, value, mat):
@@ -544,14 +550,15 @@ class SPMMMax(torch.autograd.Function):
 # Exported operators: same signatures as torch.ops.torch_sparse.spmm_{sum,mean,min,max}
 # (csrc/spmm.cpp:305-342).
 def spmm_sum(row: Optional[Tensor], rowptr: Tensor, col: Tensor, value: Optional[Tensor],
-             colptr: Optional[Tensor], csr2csc: Optional[Tensor], mat: Tensor) -> Tensor:
-    return SPMMSum.apply(row, rowptr, col, value, colptr, csr2csc, mat)
+             colptr: Optional[Tensor], csr2csc: Optional[Tensor], mat: Tensor,
+             row_csc: Optional[Tensor] = None) -> Tensor:
+    return SPMMSum.apply(row, rowptr, col, value, colptr, csr2csc, mat, row_csc)
 
 
 def spmm_mean(row: Optional[Tensor], rowptr: Tensor, col: Tensor, value: Optional[Tensor],
               rowcount: Optional[Tensor], colptr: Optional[Tensor], csr2csc: Optional[Tensor],
-              mat: Tensor) -> Tensor:
-    return SPMMMean.apply(row, rowptr, col, value, rowcount, colptr, csr2csc, mat)
+              mat: Tensor, row_csc: Optional[Tensor] = None) -> Tensor:
+    return SPMMMean.apply(row, rowptr, col, value, rowcount, colptr, csr2csc, mat, row_csc)
 
 
 def spmm_min(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor) -> Tuple[Tensor, Tensor]:

@@ -34,7 +34,7 @@ def _long_vector(t: Optional[Tensor], name: str, numel: Optional[int], device) -
 
 class SparseStorage:
     __slots__ = ("_row", "_rowptr", "_col", "_value", "_sparse_sizes", "_rowcount", "_colptr", "_colcount",
-                 "_csr2csc", "_csc2csr")
+                 "_csr2csc", "_csc2csr", "_row_csc")
 
     def __init__(self, row: Optional[Tensor] = None, rowptr: Optional[Tensor] = None,
                  col: Optional[Tensor] = None, value: Optional[Tensor] = None,
@@ -82,6 +82,7 @@ class SparseStorage:
         self._colcount = _long_vector(colcount, "colcount", N, dev)
         self._csr2csc = _long_vector(csr2csc, "csr2csc", E, dev)
         self._csc2csr = _long_vector(csc2csr, "csc2csr", E, dev)
+        self._row_csc = None  # row[csr2csc]: derived view for the SpMM backward, not one of the reference's cache keys
 
         if not is_sorted and E > 1:
             self._sort_()
@@ -104,6 +105,7 @@ class SparseStorage:
             self._value = self._value[perm]
         self._csr2csc = None
         self._csc2csr = None
+        self._row_csc = None
 
     @classmethod
     def empty(cls) -> "SparseStorage":
@@ -219,8 +221,9 @@ class SparseStorage:
         """csr2csc and colptr in one pass (torch_sparse/storage.py:369-385, 407-416)."""
         M, N = self._sparse_sizes
         if self._col.is_cuda:
-            perm, colptr, _ = ops.csr2csc(self.row(), self._col, M, N, want_colptr=True)
+            perm, colptr, row_csc = ops.csr2csc(self.row(), self._col, M, N, want_colptr=True, want_row_csc=True)
             self._csr2csc = perm
+            self._row_csc = row_csc
             if self._colptr is None:
                 self._colptr = colptr
         else:
@@ -230,6 +233,17 @@ class SparseStorage:
         if self._csr2csc is None:
             self._build_csc_()
         return self._csr2csc
+
+    def row_csc(self) -> Tensor:
+        """row[csr2csc] — the column index array of the CSC view, i.e. of A^T in CSR form. The reference gathers it
+        on every backward (csrc/spmm.cpp:104); it only depends on the structure, so it is kept (the csr2csc kernel
+        emits it for free)."""
+        if self._row_csc is None:
+            if self._csr2csc is None and self._col.is_cuda:
+                self._build_csc_()
+            if self._row_csc is None:
+                self._row_csc = self.row()[self.csr2csc()]
+        return self._row_csc
 
     def colptr(self) -> Tensor:
         if self._colptr is None:
@@ -280,6 +294,7 @@ class SparseStorage:
     def clear_cache_(self) -> "SparseStorage":
         for k in _CACHE_KEYS:
             setattr(self, "_" + k, None)
+        self._row_csc = None
         return self
 
     def cached_keys(self) -> List[str]:
