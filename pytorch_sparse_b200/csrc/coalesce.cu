@@ -6,13 +6,15 @@
 //
 // The reference issues ~12-15 ATen kernels, 3-4 host syncs and builds the linearised key twice.
 // Here:  phase 1  key = row*N+col (+ "already sorted?" flag) -> [stable CUB radix sort over only
-//                 the significant key bits, 32-bit payload] -> head flags -> DeviceSelect gives the
+//                 the significant key bits, 32-bit payload] -> DeviceSelect over on-the-fly head flags gives the
 //                 run starts and E' on the device (copied to pinned host memory);
 //        phase 2  one kernel emits row'/col' from the run heads and reduces the values of each run
 //                 in sorted (== input, the sort is stable) order.
 // A stable sort makes the float 'add' order canonical (input order); the reference's order over
 // duplicates is unspecified (non-stable Tensor.sort, torch_sparse/utils.py:19-20).
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "common.cuh"
 
@@ -38,16 +40,25 @@ __global__ void coalesce_keys_kernel(const int64_t* __restrict__ row, const int6
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(unsorted, 1);
 }
 
-__global__ void head_flags_kernel(const uint64_t* __restrict__ keys, int64_t E, uint8_t* __restrict__ flags, int ib) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride)
-    flags[i] = (i == 0 || (keys[i] >> ib) != (keys[i - 1] >> ib)) ? 1 : 0;
-}
+// head-of-run flag of sorted entry i, computed on the fly for DeviceSelect::Flagged (no flag array, no extra pass)
+struct HeadFlag {
+  const uint64_t* keys;
+  int ib;
+  __host__ __device__ __forceinline__ uint8_t operator()(uint32_t i) const {
+    return (i == 0 || (keys[i] >> ib) != (keys[i - 1] >> ib)) ? 1 : 0;
+  }
+};
 
 __global__ void copy_count_kernel(const int* __restrict__ n_sel, int64_t* __restrict__ out) { *out = (int64_t)*n_sel; }
 
-__global__ void widen_perm_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm, int64_t E,
-                                  int64_t* __restrict__ out, int ib) {
+// `sel` = {which key buffer, which payload buffer, ib}, written by the sort phase into the workspace: the
+// consumers pick the sorted buffers on the device, so phase 2 needs no read-back and no host synchronisation
+__global__ void widen_perm_kernel(const uint64_t* __restrict__ k0, const uint64_t* __restrict__ k1,
+                                  const uint32_t* __restrict__ p0, const uint32_t* __restrict__ p1,
+                                  const int* __restrict__ sel, int64_t E, int64_t* __restrict__ out) {
+  const uint64_t* keys = sel[0] ? k1 : k0;
+  const uint32_t* perm = sel[1] ? p1 : p0;
+  const int ib = sel[2];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const uint64_t mask = ib ? (((uint64_t)1 << ib) - 1) : 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += stride)
@@ -58,11 +69,15 @@ enum { C_SUM = TSB200_SUM, C_MEAN = TSB200_MEAN, C_MIN = TSB200_MIN, C_MAX = TSB
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-coalesce_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ perm,
+coalesce_emit_kernel(const uint64_t* __restrict__ k0, const uint64_t* __restrict__ k1,
+                     const uint32_t* __restrict__ p0, const uint32_t* __restrict__ p1, const int* __restrict__ sel,
                      const uint32_t* __restrict__ starts, int64_t E, int64_t N, int64_t n_unique,
                      const T* __restrict__ value_in, int64_t D, int reduce, int64_t* __restrict__ row_out,
-                     int64_t* __restrict__ col_out, T* __restrict__ value_out, int64_t* __restrict__ perm_out, int ib) {
+                     int64_t* __restrict__ col_out, T* __restrict__ value_out, int64_t* __restrict__ perm_out) {
   using acc_t = typename Traits<T>::acc_t;
+  const uint64_t* keys = sel[0] ? k1 : k0;
+  const uint32_t* perm = sel[1] ? p1 : p0;
+  const int ib = sel[2];
   const uint64_t pmask = ib ? (((uint64_t)1 << ib) - 1) : 0;
   auto perm_at = [&](int64_t j) -> int64_t { return ib ? (int64_t)(keys[j] & pmask) : (int64_t)perm[j]; };
   const int64_t total = n_unique * (value_in ? D : 1);
@@ -94,7 +109,7 @@ coalesce_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restri
 }
 
 struct CoLayout {
-  size_t k0, k1, p0, p1, flags, starts, scalars, cub, total;
+  size_t k0, k1, p0, p1, starts, scalars, cub, total;
   size_t cub_bytes;
   // scalars: [0] int unsorted, [1] int n_selected, [2..3] int64 n_unique, [4] int keys_cur, [5] int perm_cur, [6] int ib
 };
@@ -107,7 +122,6 @@ static CoLayout co_layout(int64_t E) {
   L.k1 = off; off += align_up(n * 8, 256);
   L.p0 = off; off += align_up(n * 4, 256);
   L.p1 = off; off += align_up(n * 4, 256);
-  L.flags = off; off += align_up(n, 256);
   L.starts = off; off += align_up(n * 4, 256);
   size_t t1 = 0, t2 = 0;
   cub::DoubleBuffer<uint64_t> dk(nullptr, nullptr);
@@ -118,7 +132,8 @@ static CoLayout co_layout(int64_t E) {
     cub::DeviceRadixSort::SortKeys(nullptr, t3, dk, (int)n, 0, 64, (cudaStream_t)0);
     if (t3 > t1) t1 = t3;
   }
-  cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<uint32_t>(0), (const uint8_t*)nullptr,
+  cub::DeviceSelect::Flagged(nullptr, t2, thrust::counting_iterator<uint32_t>(0),
+                             thrust::make_transform_iterator(thrust::counting_iterator<uint32_t>(0), HeadFlag{nullptr, 0}),
                              (uint32_t*)nullptr, (int*)nullptr, (int)n, (cudaStream_t)0);
   L.cub_bytes = t1 > t2 ? t1 : t2;
   L.cub = off; off += align_up(L.cub_bytes, 256);
@@ -196,12 +211,11 @@ extern "C" int tsb200_coalesce_sort(const int64_t* row, const int64_t* col, int6
   int h[3] = {cur, cur, ib};
   TSB_CUDA_TRY(cudaMemcpyAsync(sc + 4, h, sizeof(h), cudaMemcpyHostToDevice, st));
   const uint64_t* keys = cur ? k1 : k0;
-  uint8_t* flags = (uint8_t*)(ws + L.flags);
-  head_flags_kernel<<<cgrid(E), 256, 0, st>>>(keys, E, flags, ib);
-  TSB_LAUNCH_CHECK();
   size_t tb = L.cub_bytes;
-  TSB_CUDA_TRY(cub::DeviceSelect::Flagged(ws + L.cub, tb, cub::CountingInputIterator<uint32_t>(0), flags,
-                                          (uint32_t*)(ws + L.starts), sc + 1, (int)E, st));
+  TSB_CUDA_TRY(cub::DeviceSelect::Flagged(
+      ws + L.cub, tb, thrust::counting_iterator<uint32_t>(0),
+      thrust::make_transform_iterator(thrust::counting_iterator<uint32_t>(0), HeadFlag{keys, ib}),
+      (uint32_t*)(ws + L.starts), sc + 1, (int)E, st));
   copy_count_kernel<<<1, 1, 0, st>>>(sc + 1, n_unique_dev);
   TSB_LAUNCH_CHECK();
   if (n_unique_host)
@@ -220,28 +234,25 @@ extern "C" int tsb200_coalesce_emit(int64_t E, int64_t N, int64_t n_unique, cons
   cudaStream_t st = (cudaStream_t)stream;
   const CoLayout L = co_layout(E);
   const char* ws = (const char*)workspace;
-  // which half of the double buffers holds the sorted data: recorded by phase 1 on the device;
-  // phase 1 already synchronised once and the caller synchronised to read E', so a tiny D2H here
-  // is a read of settled data.
-  int h[3] = {0, 0, 0};
-  TSB_CUDA_TRY(cudaMemcpyAsync(h, ws + L.scalars + 16, sizeof(h), cudaMemcpyDeviceToHost, st));
-  TSB_CUDA_TRY(cudaStreamSynchronize(st));
-  const uint64_t* keys = (const uint64_t*)(ws + (h[0] ? L.k1 : L.k0));
-  const uint32_t* perm = (const uint32_t*)(ws + (h[1] ? L.p1 : L.p0));
+  // which half of the double buffers holds the sorted data was recorded by phase 1 in the workspace; the kernel
+  // reads it there (no read-back, no synchronisation in phase 2)
+  const uint64_t* k0 = (const uint64_t*)(ws + L.k0); const uint64_t* k1 = (const uint64_t*)(ws + L.k1);
+  const uint32_t* p0 = (const uint32_t*)(ws + L.p0); const uint32_t* p1 = (const uint32_t*)(ws + L.p1);
+  const int* sel = (const int*)(ws + L.scalars + 16);
   const uint32_t* starts = (const uint32_t*)(ws + L.starts);
-  const int ib = h[2];
   if (value_in && D == 0) value_in = nullptr;
   const int64_t total = n_unique * (value_in ? D : 1);
   if (!value_in) {
-    coalesce_emit_kernel<float><<<cgrid(total), 256, 0, st>>>(keys, perm, starts, E, N, n_unique, nullptr, 1, reduce,
-                                                             row_out, col_out, nullptr, perm_out, ib);
+    coalesce_emit_kernel<float><<<cgrid(total), 256, 0, st>>>(k0, k1, p0, p1, sel, starts, E, N, n_unique, nullptr, 1,
+                                                             reduce, row_out, col_out, nullptr, perm_out);
     TSB_LAUNCH_CHECK();
     return 0;
   }
   return dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
-    coalesce_emit_kernel<T><<<cgrid(total), 256, 0, st>>>(keys, perm, starts, E, N, n_unique, (const T*)value_in, D,
-                                                         reduce, row_out, col_out, (T*)value_out, perm_out, ib);
+    coalesce_emit_kernel<T><<<cgrid(total), 256, 0, st>>>(k0, k1, p0, p1, sel, starts, E, N, n_unique,
+                                                         (const T*)value_in, D, reduce, row_out, col_out,
+                                                         (T*)value_out, perm_out);
     TSB_LAUNCH_CHECK();
     return 0;
   });
@@ -255,12 +266,9 @@ extern "C" int tsb200_coalesce_perm(int64_t E, int64_t* perm_out, const void* wo
   cudaStream_t st = (cudaStream_t)stream;
   const CoLayout L = co_layout(E);
   const char* ws = (const char*)workspace;
-  int h[3] = {0, 0, 0};
-  TSB_CUDA_TRY(cudaMemcpyAsync(h, ws + L.scalars + 16, sizeof(h), cudaMemcpyDeviceToHost, st));
-  TSB_CUDA_TRY(cudaStreamSynchronize(st));
-  const uint64_t* keys = (const uint64_t*)(ws + (h[0] ? L.k1 : L.k0));
-  const uint32_t* perm = (const uint32_t*)(ws + (h[1] ? L.p1 : L.p0));
-  widen_perm_kernel<<<cgrid(E), 256, 0, st>>>(keys, perm, E, perm_out, h[2]);
+  widen_perm_kernel<<<cgrid(E), 256, 0, st>>>((const uint64_t*)(ws + L.k0), (const uint64_t*)(ws + L.k1),
+                                               (const uint32_t*)(ws + L.p0), (const uint32_t*)(ws + L.p1),
+                                               (const int*)(ws + L.scalars + 16), E, perm_out);
   TSB_LAUNCH_CHECK();
   return 0;
 }

@@ -262,13 +262,21 @@ def segment_reduce(ptr: Tensor, value: Tensor, reduce: str = "sum", perm: Option
 
 
 class _PinnedScalar:
-    """One pinned int64 per device-side count read back from the GPU (E', nnz(C))."""
+    """One pinned int64 per device-side count read back from the GPU (E', nnz(C)). The buffers are pooled:
+    `read()` returns the value (after the caller synchronised the stream) and hands the buffer back."""
+    _pool: list = []
 
     def __init__(self):
-        self.t = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.t = self._pool.pop() if self._pool else torch.zeros(1, dtype=torch.int64).pin_memory()
 
     def ptr(self):
         return ctypes.c_void_p(self.t.data_ptr())
+
+    def read(self) -> int:
+        v = int(self.t.item())
+        if len(self._pool) < 16:
+            self._pool.append(self.t)
+        return v
 
 
 def sort_perm(row: Tensor, col: Tensor, M: int, N: int) -> Optional[Tensor]:
@@ -316,7 +324,7 @@ def coalesce(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int,
         check(lib.tsb200_coalesce_sort(_p(row), _p(col), E, M, N, _p(ws), nws, pin.ptr(), st),
               "tsb200_coalesce_sort")
         torch.cuda.current_stream(dev).synchronize()
-        n_unique = int(pin.t.item())
+        n_unique = pin.read()
         row_out = torch.empty(n_unique, dtype=torch.int64, device=dev)
         col_out = torch.empty(n_unique, dtype=torch.int64, device=dev)
         value_out = None
@@ -363,7 +371,7 @@ def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: T
                                          nnz_b, _p(rowptr_c), _p(ws), nws, pin.ptr(), st),
               "tsb200_spspmm_symbolic")
         torch.cuda.current_stream(dev).synchronize()
-        nnz_c = int(pin.t.item())
+        nnz_c = pin.read()
         row_c = torch.empty(nnz_c, dtype=torch.int64, device=dev)
         col_c = torch.empty(nnz_c, dtype=torch.int64, device=dev)
         val_c = torch.empty(nnz_c, dtype=dtype, device=dev) if want_value else None
