@@ -70,6 +70,9 @@ def test_orthonormal_rows(dtype):
     (40, 3000, 20_000, 400, 3, torch.float32),    # A rows longer than one 256-entry batch, short B rows
     (64, 200, 1500, 20, 60, torch.float32),       # B rows longer than 32 (general path), output staged in smem
     (37, 50, 33, 5, 4, torch.float64),            # tiny window (1024 bits, 4-word scan chunks)
+    (60, 64, 9000, 45, 45, torch.float32),        # products per row straddle the 2048-entry flat/staging limit
+    (50, 300, 262_145, 10, 40, torch.float32),    # one column past a full 2^18 window: second window nearly empty
+    (20, 500, 3000, 140, 6, torch.float64),       # A rows straddle the 128-entry batch (flat vs multi-batch general)
 ])
 def test_random_vs_oracle(oracle, M, Kd, N, da, db, dtype):
     _, rpa, ca = random_csr(M, Kd, da, seed=1, empty_rows=(0,))
