@@ -81,3 +81,23 @@ def test_host_buffer_spmm(oracle):
         assert torch.equal(out, dout.cpu())
         if arg is not None:
             assert torch.equal(arg, darg.cpu())
+
+
+def test_host_buffer_spmm_chunked_pipeline():
+    """Large enough for the pipelined host path (8 row chunks over two upload streams, compute and download
+    streams): bit-identical to the device-resident call."""
+    from pytorch_sparse_b200 import ops
+    from util import fast_random_csr
+    M, N, F = 120_000, 90_000, 16
+    _, rowptr, col = fast_random_csr(M, N, 12, 7, DEV)
+    assert col.numel() >= (1 << 20)
+    g = torch.Generator(device=DEV).manual_seed(2)
+    value = torch.randn(col.numel(), generator=g, device=DEV)
+    mat = torch.randn(N, F, generator=g, device=DEV)
+    rp_h, col_h, val_h, mat_h = rowptr.cpu(), col.cpu(), value.cpu(), mat.cpu()
+    for red in ("sum", "max"):
+        ref, ref_arg = ops.spmm_fw(rowptr, col, value, mat, red)
+        out, arg = ops.spmm_fw_host(rp_h, col_h, val_h, mat_h, red)
+        assert torch.equal(out, ref.cpu()), red
+        if arg is not None:
+            assert torch.equal(arg, ref_arg.cpu()), red
