@@ -159,6 +159,9 @@ TSB200_API int tsb200_segment_reduce(const int64_t* ptr, const int64_t* perm, co
  *     semantics, call site storage.py:451). perm_out i64[E'] (optional) receives the input
  *     position of the first entry of each run.
  *   The same workspace must be passed to both phases.
+ *   Synchronisation: phase 1 synchronises `stream` once internally (it reads back an "input already sorted"
+ *   flag to skip the sort, like the reference's check at storage.py:154); phase 2 and tsb200_coalesce_perm
+ *   are fully asynchronous (they pick the sorted buffers from a selector phase 1 left in the workspace).
  * ------------------------------------------------------------------------------------------ */
 TSB200_API size_t tsb200_coalesce_workspace_bytes(int64_t E, int64_t M, int64_t N);
 TSB200_API int tsb200_coalesce_sort(const int64_t* row, const int64_t* col, int64_t E, int64_t M, int64_t N,
@@ -182,7 +185,11 @@ TSB200_API int tsb200_coalesce_perm(int64_t E, int64_t* perm_out, const void* wo
  *   Phase 2 (numeric): col_c i64[nnz], row_c i64[nnz] (may be NULL), val_c dtype[nnz] (NULL when
  *     neither input has values; a NULL val_a / val_b means all-ones). dtype in {F32, F64}
  *     (torch.sparse.mm supports only these; test/test_matmul.py:56-57).
- *   Both phases need the same workspace.
+ *   Both phases need the same workspace. Both are asynchronous on `stream`.
+ *   Preconditions (those of a SparseStorage CSR view): rowptr arrays are non-decreasing; for N > 2^18 (more than
+ *   one column window) the columns of every B row must be sorted ascending — the first and last entry of a B row
+ *   bound the windows a C row is searched in. A's rows need not be sorted; duplicates in either operand are legal
+ *   (their products are accumulated).
  * ------------------------------------------------------------------------------------------ */
 TSB200_API size_t tsb200_spspmm_workspace_bytes(int64_t M, int64_t Kd, int64_t N, int64_t nnz_a,
                                      int64_t nnz_b);
