@@ -231,6 +231,7 @@ def main():
                GOLD / "next_rows.pt")
 
     gen_next_rows2(ts, meta)
+    gen_spspmm2(ts, meta)
 
     sizes = {p.name: p.stat().st_size for p in sorted(GOLD.glob("*.pt"))}
     print("wrote", sizes, "total", sum(sizes.values()))
@@ -273,8 +274,31 @@ def gen_next_rows2(ts, meta):
     torch.save(out, GOLD / "next_rows2.pt")
 
 
+def gen_spspmm2(ts, meta):
+    """SpSpMM shapes on the limits of the CUDA kernel's row classes (flat rows hold <= 2048 products and <= 128 A
+    entries; one bitmap window is 2^18 columns), through the reference's functional API (spspmm.py:6-33)."""
+    cases = {}
+    shapes = {"p2048_f32": (24, 64, 9000, 45, 45, torch.float32),      # products per row straddle 2048
+              "na128_f64": (20, 500, 3000, 140, 6, torch.float64),     # A entries per row straddle 128
+              "window_edge_f32": (30, 300, 262_145, 10, 40, torch.float32),  # one column past a 2^18 window
+              "dups_f64": (48, 64, 96, 28, 28, torch.float64)}         # >= 3 products per output column
+    for name, (M, Kd, N, da, db, dtype) in shapes.items():
+        ra, ca = random_structure(M, Kd, da, seed=81, empty_rows=(0,))
+        rb, cb = random_structure(Kd, N, db, seed=82, empty_rows=(1,))
+        g = torch.Generator().manual_seed(83)
+        va = torch.randn(ra.numel(), generator=g).to(dtype)
+        vb = torch.randn(rb.numel(), generator=g).to(dtype)
+        ic, vc = ts.spspmm(torch.stack([ra, ca]), va, torch.stack([rb, cb]), vb, M, Kd, N)
+        cases[name] = dict(indexA=torch.stack([ra, ca]), valueA=va, indexB=torch.stack([rb, cb]), valueB=vb,
+                           M=M, K=Kd, N=N, indexC=ic, valueC=vc)
+    torch.save({"meta": meta, "cases": cases}, GOLD / "spspmm2.pt")
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "next_rows2":
+    _meta = {"reference": "rusty1s/pytorch_sparse 0.6.18 @ 91feaa5e", "torch": torch.__version__}
+    if len(sys.argv) > 1 and sys.argv[1] == "spspmm2":
+        gen_spspmm2(import_reference(), _meta)
+    elif len(sys.argv) > 1 and sys.argv[1] == "next_rows2":
         gen_next_rows2(import_reference(), {"reference": "rusty1s/pytorch_sparse 0.6.18 @ 91feaa5e", "torch": torch.__version__})
     else:
         main()
