@@ -16,7 +16,7 @@ def t(src: SparseTensor) -> SparseTensor:
     M, N = st.sparse_sizes()
     value = st.value()
     swapped = SparseStorage(
-        row=st.col()[to_csc], col=st.row()[to_csc], value=value[to_csc] if value is not None else None,
+        row=st.col()[to_csc], col=st.row_csc(), value=value[to_csc] if value is not None else None,
         sparse_sizes=(N, M),
         # CSR caches of the transpose are the CSC caches of the source and vice versa
         rowptr=st._colptr, rowcount=st._colcount, colptr=st._rowptr, colcount=st._rowcount,
