@@ -146,6 +146,14 @@ __device__ __forceinline__ float ldg_hint(const float* p, uint64_t pol) { return
 __device__ __forceinline__ double ldg_hint(const double* p, uint64_t pol) {
   return __longlong_as_double((long long)ldg64_hint(p, pol));
 }
+// predicated form: loads only when `pred`, otherwise leaves `r` untouched (the address is not dereferenced)
+__device__ __forceinline__ void ldg128_hint_pred(uint4& r, const void* p, uint64_t pol, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %6;\n\t}"
+      : "+r"(r.x), "+r"(r.y), "+r"(r.z), "+r"(r.w)
+      : "l"(p), "r"((int)pred), "l"(pol));
+}
 __device__ __forceinline__ uint4 ldg128(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"

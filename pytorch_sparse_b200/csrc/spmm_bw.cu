@@ -14,6 +14,10 @@
 
 #include "spmm_common.cuh"
 
+#ifndef TSB200_SDDMM_PREDICATED
+#define TSB200_SDDMM_PREDICATED 0
+#endif
+
 namespace tsb {
 
 template <typename T, int VEC> struct Vec16;
@@ -186,6 +190,32 @@ template <typename T, int LPR, int CH, int U> struct SddmmEngine {
       const int nst = (jend - j0 + G - 1) / G;
       const int jrel = jend - j0 - g;
       uint4 d[U][CH];
+      float part[U];
+#if TSB200_SDDMM_PREDICATED
+      // Branch-free variant (NOT enabled: written after the round's GPU budget was spent, never run — see
+      // profiles/r01_ncu_late_captures.md, the kernel is issue-bound and ~35 of its ~250 instructions per chunk are
+      // branches around the inline-asm gathers): gathers predicated inside the asm into zeroed registers, the dot
+      // products run unconditionally (an inactive slot contributes 0). The ring slot is read unconditionally — slots
+      // past the row's end hold stale but in-bounds column words, and the predicate keeps them from being dereferenced.
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const bool act = (u < nst) && (u * G < jrel);
+        const uint32_t c = pc[2 * u * G];
+        const char* src = matb + (uint64_t)c * row_bytes;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+          d[u][ch] = make_uint4(0, 0, 0, 0);
+          ldg128_hint_pred(d[u][ch], src + ch * (LPR * 16), pol, act && col_ok[ch]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float sdot = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) sdot += Vec16<T, VEC>::dot(d[u][ch], gq[ch]);
+        part[u] = sdot;
+      }
+#else
       bool act[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
@@ -198,7 +228,6 @@ template <typename T, int LPR, int CH, int U> struct SddmmEngine {
             if (col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
         }
       }
-      float part[U];
 #pragma unroll
       for (int u = 0; u < U; u++) {
         float sdot = 0.f;
@@ -209,6 +238,7 @@ template <typename T, int LPR, int CH, int U> struct SddmmEngine {
         }
         part[u] = sdot;
       }
+#endif
       // lane li of group g gets the total of step li / (LPR/U); nnz t = u*G + g of the chunk goes to lane t
       const float tot = multi_reduce<U, LPR / 2>(part, li);
       const bool mine = lane < jend - j0;
