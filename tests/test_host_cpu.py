@@ -50,6 +50,12 @@ def test_ops_reject_cpu_tensors():
     a = ts.SparseTensor(row=col, col=col, value=torch.ones(1), sparse_sizes=(1, 1))
     with pytest.raises(RuntimeError, match="must be CUDA tensor"):
         a @ torch.ones(1, 4)
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        a @ a                      # SpSpMM
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        a.to_symmetric()           # cat + coalesce: arithmetic, no CPU path
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        ts.spadd(torch.stack([col, col]), torch.ones(1), torch.stack([col, col]), torch.ones(1), 1, 1)
 
 
 def test_storage_host_bookkeeping_matches_reference_known_answers():
