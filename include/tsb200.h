@@ -142,9 +142,25 @@ TSB200_API int tsb200_csr2csc(const int64_t* row, const int64_t* col, int64_t E,
  *   `scatter(value, col, 0, None, N, reduce)` for dim=0, which on the CSC view is a segment reduce over colptr).
  *   out[s, d] = reduce_{j in [ptr[s], ptr[s+1])} value[perm ? perm[j] : j, d];  empty segment -> 0.
  *   ptr i64[S+1]; perm i64[E] or NULL; value dtype[E, D]; out dtype[S, D]; reduce in {SUM, MEAN, MIN, MAX}.
+ *   arg_out i64[S, D] (optional, MIN/MAX only): INPUT position (perm applied) of the first entry of the segment that
+ *   attains the extreme (strict compare, like csrc/cpu/reducer.h:57-70), -1 for an empty segment.
  * ------------------------------------------------------------------------------------------ */
 TSB200_API int tsb200_segment_reduce(const int64_t* ptr, const int64_t* perm, const void* value, void* out,
-                                     int64_t S, int64_t D, int dtype, int reduce, void* stream);
+                                     int64_t* arg_out, int64_t S, int64_t D, int dtype, int reduce, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of a segment / duplicate-run reduction (tsb200_segment_reduce, tsb200_coalesce_emit).  Replaces the
+ *   autograd of torch_scatter.segment_csr / scatter that the reference's value reductions ride on
+ *   (torch_sparse/storage.py:451, torch_sparse/reduce.py:36-54, torch_sparse/tensor.py:424-427).
+ *   seg i64[E]: segment id of every INPUT entry;  count i64[S] (MEAN);  arg i64[S, D] (MIN/MAX, input positions);
+ *   grad_out dtype[S, D] -> grad_in dtype[E, D] (fully written, no atomics):
+ *     SUM  grad_in[i,d] = grad_out[seg[i],d]        MEAN  ... / max(count[seg[i]], 1)
+ *     MIN/MAX  grad_in[i,d] = arg[seg[i],d] == i ? grad_out[seg[i],d] : 0
+ *   Floating dtypes only.
+ * ------------------------------------------------------------------------------------------ */
+TSB200_API int tsb200_segment_reduce_bw(const int64_t* seg, const int64_t* count, const int64_t* arg,
+                                        const void* grad_out, void* grad_in, int64_t E, int64_t S, int64_t D,
+                                        int dtype, int reduce, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * COO coalesce.  Replaces torch_sparse.coalesce -> SparseStorage.__init__ sort + .coalesce()
@@ -157,7 +173,9 @@ TSB200_API int tsb200_segment_reduce(const int64_t* ptr, const int64_t* perm, co
  *     value_in dtype[E, D] over each run of equal keys, in sorted (stable => input) order, into
  *     value_out dtype[E', D] with op in {SUM(add), MEAN, MIN, MAX} (torch_scatter.segment_csr
  *     semantics, call site storage.py:451). perm_out i64[E'] (optional) receives the input
- *     position of the first entry of each run.
+ *     position of the first entry of each run. For the backward of the value reduction (tsb200_segment_reduce_bw)
+ *     the call can also emit seg_out i64[E] (run id of every INPUT entry), count_out i64[E'] (run lengths) and
+ *     arg_out i64[E', D] (MIN/MAX: input position of the earliest entry attaining the extreme); each may be NULL.
  *   The same workspace must be passed to both phases.
  *   Synchronisation: phase 1 synchronises `stream` once internally (it reads back an "input already sorted"
  *   flag to skip the sort, like the reference's check at storage.py:154); phase 2 and tsb200_coalesce_perm
@@ -169,7 +187,8 @@ TSB200_API int tsb200_coalesce_sort(const int64_t* row, const int64_t* col, int6
                          void* stream);
 TSB200_API int tsb200_coalesce_emit(int64_t E, int64_t N, int64_t n_unique, const void* value_in, int64_t D,
                          int dtype, int reduce, int64_t* row_out, int64_t* col_out,
-                         void* value_out, int64_t* perm_out, const void* workspace, void* stream);
+                         void* value_out, int64_t* perm_out, int64_t* seg_out, int64_t* count_out,
+                         int64_t* arg_out, const void* workspace, void* stream);
 
 /* Full sorted permutation after tsb200_coalesce_sort: perm_out i64[E], perm_out[i] = input position of
  * the i-th entry in (row,col) order (stable). Replaces the sort-on-construct of SparseStorage.__init__

@@ -232,6 +232,7 @@ def main():
 
     gen_next_rows2(ts, meta)
     gen_spspmm2(ts, meta)
+    gen_grads(ts, meta)
 
     sizes = {p.name: p.stat().st_size for p in sorted(GOLD.glob("*.pt"))}
     print("wrote", sizes, "total", sum(sizes.values()))
@@ -294,11 +295,108 @@ def gen_spspmm2(ts, meta):
     torch.save({"meta": meta, "cases": cases}, GOLD / "spspmm2.pt")
 
 
+def gen_grads(ts, meta):
+    """Gradients w.r.t. the stored values through every value-carrying op that rides on coalesce / segment reduce,
+    taken from the unmodified reference's autograd (torch_scatter stand-in = plain differentiable torch ops):
+    coalesce (coalesce.py:5-25 -> storage.py:436-466), transpose (transpose.py:39-62), spadd (spadd.py:5-18),
+    add (add.py:38-56), to_symmetric (tensor.py:404-438), sum/mean/min/max over dim 0/1 (reduce.py:36-54), and a
+    GCN-normalisation flow (deg = A.sum(1); D^-1/2 A D^-1/2 @ x). Random float64 values: no ties inside a run."""
+    import torch_sparse as tsr
+    from torch_sparse import SparseTensor
+    g = torch.Generator().manual_seed(91)
+    out = {"meta": meta}
+
+    # duplicated, shuffled COO entries (same recipe as coalesce.pt)
+    M, N, E0 = 45, 38, 300
+    row = torch.randint(M, (E0,), generator=g)
+    col = torch.randint(N, (E0,), generator=g)
+    reps = torch.randint(1, 4, (E0,), generator=g)
+    row, col = row.repeat_interleave(reps), col.repeat_interleave(reps)
+    perm = torch.randperm(row.numel(), generator=g)
+    index = torch.stack([row[perm], col[perm]])
+    E = index.size(1)
+    v1 = torch.randn(E, generator=g, dtype=torch.float64)
+    v2 = torch.randn(E, 3, generator=g, dtype=torch.float64)
+    co = {"in": dict(index=index, v1=v1, v2=v2, M=M, N=N)}
+    for tag, v in (("v1", v1), ("v2", v2)):
+        for op in ("add", "mean", "min", "max"):
+            vv = v.clone().requires_grad_()
+            oi, ov = tsr.coalesce(index, vv, M, N, op=op)
+            go = torch.randn(ov.shape, generator=g, dtype=torch.float64)
+            ov.backward(go)
+            co[f"{tag}_{op}"] = dict(index=oi, value=ov.detach(), grad_out=go, grad_value=vv.grad.clone())
+    vv = v1.clone().requires_grad_()
+    ti, tv = tsr.transpose(index, vv, M, N)
+    go = torch.randn(tv.shape, generator=g, dtype=torch.float64)
+    tv.backward(go)
+    co["transpose"] = dict(index=ti, value=tv.detach(), grad_out=go, grad_value=vv.grad.clone())
+    out["coalesce"] = co
+
+    # coalesced operands: spadd / add / to_symmetric / reductions
+    M, N = 36, 36
+    ra, ca = random_structure(M, N, 5, seed=92, empty_rows=(0, 9))
+    rb, cb = random_structure(M, N, 4, seed=93, empty_rows=(4,))
+    va = torch.randn(ra.numel(), generator=g, dtype=torch.float64)
+    vb = torch.randn(rb.numel(), generator=g, dtype=torch.float64)
+    va2 = torch.randn(ra.numel(), 2, generator=g, dtype=torch.float64)
+    ops = {"in": dict(ra=ra, ca=ca, va=va, va2=va2, rb=rb, cb=cb, vb=vb, M=M, N=N)}
+
+    a, b = va.clone().requires_grad_(), vb.clone().requires_grad_()
+    si, sv = tsr.spadd(torch.stack([ra, ca]), a, torch.stack([rb, cb]), b, M, N)
+    go = torch.randn(sv.shape, generator=g, dtype=torch.float64)
+    sv.backward(go)
+    ops["spadd"] = dict(index=si, value=sv.detach(), grad_out=go, grad_a=a.grad.clone(), grad_b=b.grad.clone())
+
+    a, b = va.clone().requires_grad_(), vb.clone().requires_grad_()
+    C = tsr.add(SparseTensor(row=ra, col=ca, value=a, sparse_sizes=(M, N)),
+                SparseTensor(row=rb, col=cb, value=b, sparse_sizes=(M, N)))
+    cv = C.storage.value()
+    go = torch.randn(cv.shape, generator=g, dtype=torch.float64)
+    cv.backward(go)
+    ops["add"] = dict(row=C.storage.row(), col=C.storage.col(), value=cv.detach(), grad_out=go,
+                      grad_a=a.grad.clone(), grad_b=b.grad.clone())
+
+    for tag, v in (("v", va), ("v2", va2)):
+        for red in ("sum", "mean", "min", "max"):
+            a = v.clone().requires_grad_()
+            S = SparseTensor(row=ra, col=ca, value=a, sparse_sizes=(M, N)).to_symmetric(red)
+            sv = S.storage.value()
+            go = torch.randn(sv.shape, generator=g, dtype=torch.float64)
+            sv.backward(go)
+            ops[f"sym_{red}_{tag}"] = dict(row=S.storage.row(), col=S.storage.col(), value=sv.detach(), grad_out=go,
+                                           grad_value=a.grad.clone())
+            for dim in (0, 1):
+                a = v.clone().requires_grad_()
+                r = getattr(tsr, red)(SparseTensor(row=ra, col=ca, value=a, sparse_sizes=(M, N)), dim)
+                go = torch.randn(r.shape, generator=g, dtype=torch.float64)
+                r.backward(go)
+                ops[f"reduce_{red}_{dim}_{tag}"] = dict(out=r.detach(), grad_out=go, grad_value=a.grad.clone())
+    out["ops"] = ops
+
+    # GCN normalisation: deg = A.sum(1); A_hat = D^-1/2 A D^-1/2; y = A_hat @ x  (learnable edge weights)
+    a = va.abs().add(0.1).requires_grad_()
+    x = torch.randn(N, 5, generator=g, dtype=torch.float64, requires_grad=True)
+    A = SparseTensor(row=ra, col=ca, value=a, sparse_sizes=(M, N))
+    deg = tsr.sum(A, dim=1)
+    dis = deg.pow(-0.5)
+    dis = dis.masked_fill(dis == float("inf"), 0.0)
+    Ah = tsr.mul(tsr.mul(A, dis.view(-1, 1)), dis.view(1, -1))
+    y = Ah @ x
+    go = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(go)
+    out["gcn"] = dict(value=a.detach().clone(), x=x.detach().clone(), y=y.detach(), grad_out=go,
+                      grad_value=a.grad.clone(), grad_x=x.grad.clone())
+    torch.save(out, GOLD / "grads.pt")
+    print("grads.pt", (GOLD / "grads.pt").stat().st_size)
+
+
 if __name__ == "__main__":
     _meta = {"reference": "rusty1s/pytorch_sparse 0.6.18 @ 91feaa5e", "torch": torch.__version__}
     if len(sys.argv) > 1 and sys.argv[1] == "spspmm2":
         gen_spspmm2(import_reference(), _meta)
     elif len(sys.argv) > 1 and sys.argv[1] == "next_rows2":
         gen_next_rows2(import_reference(), {"reference": "rusty1s/pytorch_sparse 0.6.18 @ 91feaa5e", "torch": torch.__version__})
+    elif len(sys.argv) > 1 and sys.argv[1] == "grads":
+        gen_grads(import_reference(), _meta)
     else:
         main()

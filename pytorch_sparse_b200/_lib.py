@@ -37,9 +37,13 @@ SIGNATURES = {
     "tsb200_coalesce_sort": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_size_t,
                                      c_void_p, c_void_p]),
     "tsb200_coalesce_emit": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_int,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
     "tsb200_coalesce_perm": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
-    "tsb200_segment_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "tsb200_segment_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
+                                      c_void_p]),
+    "tsb200_segment_reduce_bw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                         c_int, c_int, c_void_p]),
     "tsb200_spspmm_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int64]),
     "tsb200_spspmm_symbolic": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                        c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -73,7 +73,8 @@ coalesce_emit_kernel(const uint64_t* __restrict__ k0, const uint64_t* __restrict
                      const uint32_t* __restrict__ p0, const uint32_t* __restrict__ p1, const int* __restrict__ sel,
                      const uint32_t* __restrict__ starts, int64_t E, int64_t N, int64_t n_unique,
                      const T* __restrict__ value_in, int64_t D, int reduce, int64_t* __restrict__ row_out,
-                     int64_t* __restrict__ col_out, T* __restrict__ value_out, int64_t* __restrict__ perm_out) {
+                     int64_t* __restrict__ col_out, T* __restrict__ value_out, int64_t* __restrict__ perm_out,
+                     int64_t* __restrict__ seg_out, int64_t* __restrict__ count_out, int64_t* __restrict__ arg_out) {
   using acc_t = typename Traits<T>::acc_t;
   const uint64_t* keys = sel[0] ? k1 : k0;
   const uint32_t* perm = sel[1] ? p1 : p0;
@@ -93,17 +94,24 @@ coalesce_emit_kernel(const uint64_t* __restrict__ k0, const uint64_t* __restrict
       if (row_out) row_out[seg] = (int64_t)r;
       if (col_out) col_out[seg] = (int64_t)(k - r * (uint64_t)N);
       if (perm_out) perm_out[seg] = perm_at(s);
+      if (count_out) count_out[seg] = e - s;
+      // run id of every INPUT entry: what the backward of the value reduction gathers through
+      if (seg_out)
+        for (int64_t j = s; j < e; j++) seg_out[perm_at(j)] = seg;
     }
     if (value_in) {
-      acc_t a = Traits<T>::to_acc(value_in[perm_at(s) * D + d]);
+      int64_t first = perm_at(s);
+      acc_t a = Traits<T>::to_acc(value_in[first * D + d]);
       for (int64_t j = s + 1; j < e; j++) {
-        const acc_t v = Traits<T>::to_acc(value_in[perm_at(j) * D + d]);
+        const int64_t pj = perm_at(j);
+        const acc_t v = Traits<T>::to_acc(value_in[pj * D + d]);
         if (reduce == C_SUM || reduce == C_MEAN) a = a + v;
-        else if (reduce == C_MIN) a = v < a ? v : a;
-        else a = v > a ? v : a;
+        else if (reduce == C_MIN) { if (v < a) { a = v; first = pj; } }   // strict: ties keep the earliest input entry
+        else { if (v > a) { a = v; first = pj; } }
       }
       if (reduce == C_MEAN) a = a / (acc_t)(e - s);
       value_out[seg * D + d] = Traits<T>::from_acc(a);
+      if (arg_out) arg_out[seg * D + d] = first;
     }
   }
 }
@@ -225,7 +233,8 @@ extern "C" int tsb200_coalesce_sort(const int64_t* row, const int64_t* col, int6
 
 extern "C" int tsb200_coalesce_emit(int64_t E, int64_t N, int64_t n_unique, const void* value_in, int64_t D,
                                     int dtype, int reduce, int64_t* row_out, int64_t* col_out, void* value_out,
-                                    int64_t* perm_out, const void* workspace, void* stream) {
+                                    int64_t* perm_out, int64_t* seg_out, int64_t* count_out, int64_t* arg_out,
+                                    const void* workspace, void* stream) {
   if (E < 0 || N < 0 || n_unique < 0 || n_unique > E) return TSB200_ERR_INVALID_ARG;
   if (n_unique == 0) return 0;
   if (!workspace) return TSB200_ERR_WORKSPACE;
@@ -244,7 +253,8 @@ extern "C" int tsb200_coalesce_emit(int64_t E, int64_t N, int64_t n_unique, cons
   const int64_t total = n_unique * (value_in ? D : 1);
   if (!value_in) {
     coalesce_emit_kernel<float><<<cgrid(total), 256, 0, st>>>(k0, k1, p0, p1, sel, starts, E, N, n_unique, nullptr, 1,
-                                                             reduce, row_out, col_out, nullptr, perm_out);
+                                                             reduce, row_out, col_out, nullptr, perm_out, seg_out,
+                                                             count_out, nullptr);
     TSB_LAUNCH_CHECK();
     return 0;
   }
@@ -252,7 +262,8 @@ extern "C" int tsb200_coalesce_emit(int64_t E, int64_t N, int64_t n_unique, cons
     using T = decltype(tag);
     coalesce_emit_kernel<T><<<cgrid(total), 256, 0, st>>>(k0, k1, p0, p1, sel, starts, E, N, n_unique,
                                                          (const T*)value_in, D, reduce, row_out, col_out,
-                                                         (T*)value_out, perm_out);
+                                                         (T*)value_out, perm_out, seg_out, count_out,
+                                                         (reduce == C_MIN || reduce == C_MAX) ? arg_out : nullptr);
     TSB_LAUNCH_CHECK();
     return 0;
   });

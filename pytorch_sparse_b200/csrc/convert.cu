@@ -95,7 +95,7 @@ __global__ void colptr_kernel(const uint32_t* __restrict__ sorted_col, int64_t E
 template <typename T>
 __global__ void __launch_bounds__(256)
 segment_reduce_kernel(const int64_t* __restrict__ ptr, const int64_t* __restrict__ perm, const T* __restrict__ value,
-                      T* __restrict__ out, int64_t S, int64_t D, int reduce) {
+                      T* __restrict__ out, int64_t* __restrict__ arg_out, int64_t S, int64_t D, int reduce) {
   using acc_t = typename Traits<T>::acc_t;
   const int lane = threadIdx.x & 31;
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -105,30 +105,63 @@ segment_reduce_kernel(const int64_t* __restrict__ ptr, const int64_t* __restrict
     for (int64_t d = 0; d < D; d++) {
       acc_t a = (acc_t)0;
       bool have = false;
+      // (jpos, asrc): position inside the segment and input position of this lane's current extreme; a tie between
+      // lanes goes to the smaller position, so the arg is the FIRST entry of the segment that attains the extreme
+      // (torch_scatter's strict-compare rule, same as csrc/cpu/reducer.h:57-70 for SpMM)
+      int64_t jpos = -1, asrc = -1;
       for (int64_t j = b + lane; j < e; j += 32) {
         const int64_t src = perm ? __ldg(perm + j) : j;
         const acc_t v = Traits<T>::to_acc(value[src * D + d]);
-        if (!have) { a = v; have = true; }
+        if (!have) { a = v; have = true; jpos = j; asrc = src; }
         else if (reduce == TSB200_SUM || reduce == TSB200_MEAN) a = a + v;
-        else if (reduce == TSB200_MIN) a = v < a ? v : a;
-        else a = v > a ? v : a;
+        else if (reduce == TSB200_MIN) { if (v < a) { a = v; jpos = j; asrc = src; } }
+        else { if (v > a) { a = v; jpos = j; asrc = src; } }
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         const acc_t o = __shfl_down_sync(0xffffffffu, a, off);
         const bool oh = __shfl_down_sync(0xffffffffu, (int)have, off) != 0;
+        const int64_t oj = __shfl_down_sync(0xffffffffu, jpos, off);
+        const int64_t os = __shfl_down_sync(0xffffffffu, asrc, off);
         if (oh) {
-          if (!have) { a = o; have = true; }
+          if (!have) { a = o; have = true; jpos = oj; asrc = os; }
           else if (reduce == TSB200_SUM || reduce == TSB200_MEAN) a = a + o;
-          else if (reduce == TSB200_MIN) a = o < a ? o : a;
-          else a = o > a ? o : a;
+          else if (reduce == TSB200_MIN) { if (o < a || (o == a && oj < jpos)) { a = o; jpos = oj; asrc = os; } }
+          else { if (o > a || (o == a && oj < jpos)) { a = o; jpos = oj; asrc = os; } }
         }
       }
       if (lane == 0) {
         if (reduce == TSB200_MEAN && e > b) a = a / (acc_t)(e - b);
         out[seg * D + d] = Traits<T>::from_acc(have ? a : (acc_t)0);
+        if (arg_out) arg_out[seg * D + d] = have ? asrc : (int64_t)-1;
       }
     }
+  }
+}
+
+// Backward of the segment / run reductions (segment_reduce, coalesce): a pure gather, no atomics.
+//   sum : grad_in[i,d] = grad_out[seg[i],d]            mean: ... / max(count[seg[i]],1)
+//   min/max: grad_in[i,d] = (arg[seg[i],d] == i) ? grad_out[seg[i],d] : 0
+// (torch_scatter's segment_csr / scatter backward as reached from torch_sparse/storage.py:451 and reduce.py:36-54.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_reduce_bw_kernel(const int64_t* __restrict__ seg, const int64_t* __restrict__ count,
+                         const int64_t* __restrict__ arg, const T* __restrict__ grad_out, T* __restrict__ grad_in,
+                         int64_t E, int64_t D, int reduce) {
+  using acc_t = typename Traits<T>::acc_t;
+  const int64_t total = E * D;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t i = t / D, d = t - i * D;
+    const int64_t s = __ldg(seg + i);
+    acc_t g = Traits<T>::to_acc(grad_out[s * D + d]);
+    if (reduce == TSB200_MEAN) {
+      const int64_t c = __ldg(count + s);
+      g = g / (acc_t)(c > 0 ? c : 1);
+    } else if (reduce == TSB200_MIN || reduce == TSB200_MAX) {
+      if (__ldg(arg + s * D + d) != i) g = (acc_t)0;
+    }
+    grad_in[t] = Traits<T>::from_acc(g);
   }
 }
 
@@ -224,15 +257,35 @@ extern "C" int tsb200_csr2csc(const int64_t* row, const int64_t* col, int64_t E,
   return 0;
 }
 
-extern "C" int tsb200_segment_reduce(const int64_t* ptr, const int64_t* perm, const void* value, void* out, int64_t S,
-                                     int64_t D, int dtype, int reduce, void* stream) {
+extern "C" int tsb200_segment_reduce(const int64_t* ptr, const int64_t* perm, const void* value, void* out,
+                                     int64_t* arg_out, int64_t S, int64_t D, int dtype, int reduce, void* stream) {
   if (S < 0 || D < 0 || reduce < TSB200_SUM || reduce > TSB200_MAX) return TSB200_ERR_INVALID_ARG;
   if (S == 0 || D == 0) return 0;
   if (!ptr || !out) return TSB200_ERR_INVALID_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   return dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
-    segment_reduce_kernel<T><<<grid1d(S * 32, 256), 256, 0, st>>>(ptr, perm, (const T*)value, (T*)out, S, D, reduce);
+    segment_reduce_kernel<T><<<grid1d(S * 32, 256), 256, 0, st>>>(
+        ptr, perm, (const T*)value, (T*)out, (reduce == TSB200_MIN || reduce == TSB200_MAX) ? arg_out : nullptr, S, D,
+        reduce);
+    TSB_LAUNCH_CHECK();
+    return 0;
+  });
+}
+
+extern "C" int tsb200_segment_reduce_bw(const int64_t* seg, const int64_t* count, const int64_t* arg,
+                                        const void* grad_out, void* grad_in, int64_t E, int64_t S, int64_t D,
+                                        int dtype, int reduce, void* stream) {
+  if (E < 0 || S < 0 || D < 0 || reduce < TSB200_SUM || reduce > TSB200_MAX) return TSB200_ERR_INVALID_ARG;
+  if (E == 0 || D == 0) return 0;
+  if (!seg || !grad_out || !grad_in) return TSB200_ERR_INVALID_ARG;
+  if (reduce == TSB200_MEAN && !count) return TSB200_ERR_INVALID_ARG;
+  if ((reduce == TSB200_MIN || reduce == TSB200_MAX) && !arg) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dispatch_float_dtype(dtype, [&](auto tag) -> int {
+    using T = decltype(tag);
+    segment_reduce_bw_kernel<T><<<grid1d(E * D, 256), 256, 0, st>>>(seg, count, arg, (const T*)grad_out, (T*)grad_in,
+                                                                   E, D, reduce);
     TSB_LAUNCH_CHECK();
     return 0;
   });

@@ -33,9 +33,15 @@ def spmm(index: Tensor, value: Tensor, m: int, n: int, matrix: Tensor) -> Tensor
 
 
 def spspmm(indexA, valueA, indexB, valueB, m, k, n, coalesced=False):
-    """Sparse (m x k) times sparse (k x n) -> (index, value) of the sorted, coalesced product."""
-    A = SparseTensor(row=indexA[0], col=indexA[1], value=valueA, sparse_sizes=(m, k), is_sorted=not coalesced)
-    B = SparseTensor(row=indexB[0], col=indexB[1], value=valueB, sparse_sizes=(k, n), is_sorted=not coalesced)
+    """Sparse (m x k) times sparse (k x n) -> (index, value) of the sorted, coalesced product.
+
+    The reference passes `is_sorted=not coalesced` and then hands COO to torch.sparse.mm, which tolerates
+    unsorted / uncoalesced indices either way (torch_sparse/spspmm.py:25-28). Here the product runs on the
+    CSR views, which need row-major order, so the order is always verified: the native check is one kernel
+    and returns without sorting when the entries are already ordered. Duplicate entries need no merging —
+    their products accumulate, as in torch.sparse.mm."""
+    A = SparseTensor(row=indexA[0], col=indexA[1], value=valueA, sparse_sizes=(m, k), is_sorted=False)
+    B = SparseTensor(row=indexB[0], col=indexB[1], value=valueB, sparse_sizes=(k, n), is_sorted=False)
     C = matmul(A, B)
     row, col, value = C.coo()
     return torch.stack([row, col], dim=0), value

@@ -240,25 +240,81 @@ def csr2csc(row: Tensor, col: Tensor, M: int, N: int, want_colptr: bool = True,
     return perm, colptr, row_csc
 
 
-def segment_reduce(ptr: Tensor, value: Tensor, reduce: str = "sum", perm: Optional[Tensor] = None) -> Tensor:
-    """out[s] = reduce(value[perm?][ptr[s]:ptr[s+1]]) along dim 0, empty segments -> 0
-    (torch_scatter.segment_csr as used by torch_sparse/reduce.py:36-54)."""
+def _segment_reduce_raw(ptr: Tensor, value: Tensor, reduce: str, perm: Optional[Tensor],
+                        want_arg: bool) -> Tuple[Tensor, Optional[Tensor]]:
     _check_cuda(ptr, "ptr")
     _check_cuda(value, "value")
     ptr = _i64(ptr, "ptr")
     value = value.contiguous()
+    red = _reduce_code(reduce)
     S = ptr.numel() - 1
     E = value.size(0)
     D = value.numel() // E if E > 0 else int(torch.Size(value.shape[1:]).numel())
     out = torch.zeros((S,) + tuple(value.shape[1:]), dtype=value.dtype, device=value.device)
+    arg = None
+    if want_arg and red >= 2:
+        arg = torch.full(out.shape, -1, dtype=torch.int64, device=value.device)
     if S == 0 or D == 0 or E == 0:
-        return out
+        return out, arg
     if perm is not None:
         perm = _i64(perm, "perm")
     with _on_device(value.device):
-        check(lib.tsb200_segment_reduce(_p(ptr), _p(perm), _p(value), _p(out), S, D, _dtype_code(value.dtype),
-                                        _reduce_code(reduce), _stream(value.device)), "tsb200_segment_reduce")
-    return out
+        check(lib.tsb200_segment_reduce(_p(ptr), _p(perm), _p(value), _p(out), _p(arg), S, D,
+                                        _dtype_code(value.dtype), red, _stream(value.device)),
+              "tsb200_segment_reduce")
+    return out, arg
+
+
+def segment_reduce_bw(seg: Tensor, count: Optional[Tensor], arg: Optional[Tensor], grad_out: Tensor, E: int,
+                      reduce: str) -> Tensor:
+    """Gradient of a segment / duplicate-run reduction w.r.t. its E input entries (tsb200_segment_reduce_bw):
+    the autograd of torch_scatter.segment_csr / scatter that torch_sparse/storage.py:451 and
+    torch_sparse/reduce.py:36-54 rely on, as one gather kernel."""
+    _check_cuda(grad_out, "grad_out")
+    grad_out = grad_out.contiguous()
+    S = grad_out.size(0)
+    D = grad_out.numel() // S if S > 0 else int(torch.Size(grad_out.shape[1:]).numel())
+    grad_in = torch.empty((E,) + tuple(grad_out.shape[1:]), dtype=grad_out.dtype, device=grad_out.device)
+    if E == 0 or D == 0:
+        return grad_in
+    if not grad_out.dtype.is_floating_point:
+        raise RuntimeError("segment_reduce backward needs a floating point dtype")
+    with _on_device(grad_out.device):
+        check(lib.tsb200_segment_reduce_bw(_p(seg), _p(count), _p(arg), _p(grad_out), _p(grad_in), E, S, D,
+                                           _dtype_code(grad_out.dtype), _reduce_code(reduce),
+                                           _stream(grad_out.device)), "tsb200_segment_reduce_bw")
+    return grad_in
+
+
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, ptr, reduce, perm, seg):
+        out, arg = _segment_reduce_raw(ptr, value, reduce, perm, want_arg=True)
+        ctx.reduce = reduce
+        ctx.E = value.size(0)
+        if seg is None:  # segment id of every input entry
+            seg = ptr2ind(ptr, ctx.E)
+            if perm is not None:
+                seg = torch.empty_like(seg).scatter_(0, perm, seg)
+        count = (ptr[1:] - ptr[:-1]) if _reduce_code(reduce) == 1 else None
+        ctx.save_for_backward(seg, count, arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        seg, count, arg = ctx.saved_tensors
+        return segment_reduce_bw(seg, count, arg, grad_out, ctx.E, ctx.reduce), None, None, None, None
+
+
+def segment_reduce(ptr: Tensor, value: Tensor, reduce: str = "sum", perm: Optional[Tensor] = None,
+                   seg: Optional[Tensor] = None) -> Tensor:
+    """out[s] = reduce(value[perm?][ptr[s]:ptr[s+1]]) along dim 0, empty segments -> 0
+    (torch_scatter.segment_csr as used by torch_sparse/reduce.py:36-54). Differentiable in `value`
+    like the reference's; `seg` (segment id of every entry of `value`, e.g. the COO row / col vector)
+    is an optional hint that saves rebuilding it for the backward."""
+    if value.requires_grad and torch.is_grad_enabled():
+        return _SegmentReduce.apply(value, ptr, reduce, perm, seg)
+    return _segment_reduce_raw(ptr, value, reduce, perm, want_arg=False)[0]
 
 
 class _PinnedScalar:
@@ -301,10 +357,10 @@ def sort_perm(row: Tensor, col: Tensor, M: int, N: int) -> Optional[Tensor]:
     return perm
 
 
-def coalesce(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int,
-             reduce: str = "add") -> Tuple[Tensor, Tensor, Optional[Tensor]]:
-    """Sort by (row, col), merge duplicate entries, reduce their values
-    (torch_sparse/coalesce.py:5-25 -> torch_sparse/storage.py:149-162, 436-466)."""
+def _coalesce_raw(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int, reduce: str,
+                  want_bw: bool):
+    """-> (row', col', value', (seg, count, arg) or None). `want_bw` also emits what the backward of the value
+    reduction reads: the run id of every input entry, the run lengths (mean) and the arg entry (min/max)."""
     _check_cuda(row, "row")
     _check_cuda(col, "col")
     row, col = _i64(row, "row"), _i64(col, "col")
@@ -315,7 +371,7 @@ def coalesce(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int,
         _check_input(value.size(0) == E)
         value = value.contiguous()
     if E == 0:
-        return row, col, value
+        return row, col, value, None
     with _on_device(dev):
         nws = lib.tsb200_coalesce_workspace_bytes(E, M, N)
         ws = _workspace(nws, dev)
@@ -333,9 +389,47 @@ def coalesce(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int,
             D = value.numel() // E
             dt = _dtype_code(value.dtype)
             value_out = torch.empty((n_unique,) + tuple(value.shape[1:]), dtype=value.dtype, device=dev)
+        seg = count = arg = None
+        if want_bw and value is not None:
+            seg = torch.empty(E, dtype=torch.int64, device=dev)
+            if red == 1:
+                count = torch.empty(n_unique, dtype=torch.int64, device=dev)
+            if red >= 2:
+                arg = torch.empty(value_out.shape, dtype=torch.int64, device=dev)
         check(lib.tsb200_coalesce_emit(E, N, n_unique, _p(value), D, dt, red, _p(row_out), _p(col_out),
-                                       _p(value_out), None, _p(ws), st), "tsb200_coalesce_emit")
-    return row_out, col_out, value_out
+                                       _p(value_out), None, _p(seg), _p(count), _p(arg), _p(ws), st),
+              "tsb200_coalesce_emit")
+    return row_out, col_out, value_out, ((seg, count, arg) if seg is not None else None)
+
+
+class _Coalesce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, row, col, M, N, reduce):
+        row_out, col_out, value_out, bw = _coalesce_raw(row, col, value, M, N, reduce, want_bw=True)
+        ctx.reduce = reduce
+        ctx.E = value.size(0)
+        ctx.identity = bw is None          # E == 0: value passes through
+        if bw is not None:
+            ctx.save_for_backward(*bw)
+        ctx.mark_non_differentiable(row_out, col_out)
+        return row_out, col_out, value_out
+
+    @staticmethod
+    def backward(ctx, _g_row, _g_col, grad_value):
+        if ctx.identity:
+            return grad_value, None, None, None, None, None
+        seg, count, arg = ctx.saved_tensors
+        return segment_reduce_bw(seg, count, arg, grad_value, ctx.E, ctx.reduce), None, None, None, None, None
+
+
+def coalesce(row: Tensor, col: Tensor, value: Optional[Tensor], M: int, N: int,
+             reduce: str = "add") -> Tuple[Tensor, Tensor, Optional[Tensor]]:
+    """Sort by (row, col), merge duplicate entries, reduce their values
+    (torch_sparse/coalesce.py:5-25 -> torch_sparse/storage.py:149-162, 436-466). Differentiable in `value`
+    (the reference's value reduction is torch_scatter.segment_csr, storage.py:451)."""
+    if value is not None and value.requires_grad and torch.is_grad_enabled():
+        return _Coalesce.apply(value, row, col, M, N, reduce)
+    return _coalesce_raw(row, col, value, M, N, reduce, want_bw=False)[:3]
 
 
 def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: Tensor, col_b: Tensor,

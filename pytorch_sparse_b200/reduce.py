@@ -2,7 +2,8 @@
 (torch_sparse/reduce.py:8-93). dim=1 reduces each row's stored values (a segment reduce over `rowptr`),
 dim=0 each column's (a segment reduce over `colptr` through the `csr2csc` permutation, instead of the
 reference's scatter over `col`), dim>1 reduces trailing value dimensions, dim=None everything.
-Without values the entries count as ones."""
+Without values the entries count as ones. Gradients flow to the stored values as in the reference (whose
+segment_csr / scatter are differentiable): ops.segment_reduce is an autograd Function with a one-kernel backward."""
 from __future__ import annotations
 
 from typing import Optional
@@ -38,9 +39,11 @@ def reduction(src: SparseTensor, dim: Optional[int] = None, reduce: str = "sum")
             return (st.rowcount() if dim == 1 else st.colcount()).to(src.dtype())
         # one result per column (dim=0) or per row (dim=1)
         return torch.ones(src.size(1) if dim == 0 else src.size(0), dtype=src.dtype(), device=src.device())
+    # the segment id of every stored entry is its COO row (dim=1) / column (dim=0): what the backward gathers through
+    grad = value.requires_grad and torch.is_grad_enabled()
     if dim == 1:
-        return ops.segment_reduce(st.rowptr(), value, reduce)
-    return ops.segment_reduce(st.colptr(), value, reduce, perm=st.csr2csc())
+        return ops.segment_reduce(st.rowptr(), value, reduce, seg=st.row() if grad else None)
+    return ops.segment_reduce(st.colptr(), value, reduce, perm=st.csr2csc(), seg=st.col() if grad else None)
 
 
 def sum(src: SparseTensor, dim: Optional[int] = None) -> Tensor:  # noqa: A001
