@@ -65,6 +65,12 @@ TSB200_API int tsb200_version(void);
 TSB200_API const char* tsb200_strerror(int code);
 /* 0 iff a CUDA device with compute capability 10.x is current. */
 TSB200_API int tsb200_device_ok(void);
+/* CUDA toolkit version the library was built with, CUDA_VERSION encoding (12090 = 12.9). Replaces
+ * torch.ops.torch_sparse.cuda_version() (csrc/version.cpp:27-41), read by the import-time check at
+ * torch_sparse/__init__.py:23-37. */
+TSB200_API int tsb200_cuda_version(void);
+/* Multiprocessor count of the current device (grids are sized from it at run time). */
+TSB200_API int tsb200_sm_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * CSR SpMM forward.   Replaces spmm_fw -> spmm_cpu / spmm_cuda
@@ -226,7 +232,8 @@ TSB200_API int tsb200_spspmm_numeric(const int64_t* rowptr_a, const int64_t* col
  * Host-buffer SpMM (the end-to-end call a reference-side binding makes with CPU tensors):
  * all `_host` pointers are HOST memory (pinned for full speed, pageable works); the call stages
  * them to the current device, runs tsb200_spmm_fw and copies out (and arg_out) back. Synchronous.
- * Same semantics/argument meaning as tsb200_spmm_fw.
+ * Same semantics/argument meaning as tsb200_spmm_fw. Staging resources are kept per device: calls on different
+ * devices run concurrently, calls on one device serialise; on an error return no copy of the call is in flight.
  * ------------------------------------------------------------------------------------------ */
 TSB200_API int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* col_host,
                         const void* value_host, const void* mat_host, void* out_host,

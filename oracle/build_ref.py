@@ -56,12 +56,29 @@ def _one(item):
     return so
 
 
+REF_TESTS = ["test_matmul.py", "test_spmm.py", "test_spspmm.py", "test_coalesce.py", "test_storage.py",
+             "test_transpose.py", "test_add.py", "test_mul.py", "test_tensor.py", "test_overload.py"]
+
+
+def stage_tests() -> Path:
+    """Stage the reference's own test files for the hot path, byte for byte, next to its compiled operators in
+    oracle/_ref/ref_tests/ (git-ignored: they never enter this repo's history, but travel to the GPU box, where
+    tests/test_reference_suite_gpu.py runs them unmodified against pytorch_sparse_b200)."""
+    import shutil
+    dst = OUT / "ref_tests"
+    dst.mkdir(parents=True, exist_ok=True)
+    for name in REF_TESTS:
+        shutil.copyfile(REF / "test" / name, dst / name)
+    return dst
+
+
 def build() -> Path:
     if not (REF / "csrc/cpu/spmm_cpu.cpp").exists():
         raise FileNotFoundError(f"{REF} not present (the GPU box uses the prebuilt oracle/_ref)")
     OUT.mkdir(parents=True, exist_ok=True)
     with ThreadPoolExecutor(max_workers=3) as ex:
         list(ex.map(_one, LIBS.items()))
+    stage_tests()
     return OUT
 
 

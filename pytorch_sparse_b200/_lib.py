@@ -18,6 +18,8 @@ SIGNATURES = {
     "tsb200_version": (c_int, []),
     "tsb200_strerror": (c_char_p, [c_int]),
     "tsb200_device_ok": (c_int, []),
+    "tsb200_cuda_version": (c_int, []),
+    "tsb200_sm_count": (c_int, []),
     "tsb200_spmm_fw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int, c_int]),
     "tsb200_spmm_fw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int,

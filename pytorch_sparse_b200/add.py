@@ -1,7 +1,8 @@
 """Sparse + sparse addition: `spadd(indexA, valueA, indexB, valueB, m, n)` and `add(SparseTensor, SparseTensor)`
 (torch_sparse/spadd.py:5-18, torch_sparse/add.py:38-56) — both are "concatenate the entries, coalesce with
 sum", so they ride on the native coalesce kernels. `narrow` slices rows (pointer arithmetic) or columns
-(torch_sparse/narrow.py:8-77)."""
+(torch_sparse/narrow.py:8-77). `mul` / `mul_` / `mul_nnz` and the dense-vector `add` variants
+(torch_sparse/mul.py, add.py:21-37, 59-104) complete the row/column scaling family."""
 from __future__ import annotations
 
 from typing import Optional
@@ -22,9 +23,27 @@ def spadd(indexA, valueA, indexB, valueB, m, n):
     return torch.stack([row, col], dim=0), value
 
 
-def add(src: SparseTensor, other: SparseTensor) -> SparseTensor:
+def _broadcast_to_nnz(src: SparseTensor, other: Tensor) -> Tensor:
+    """`other` of shape [M, 1, ...] (one factor per row) or [1, N, ...] (per column) expanded to one per stored entry
+    (torch_sparse/add.py:24-31, mul.py:24-33: gather_csr over rowptr / a gather through col)."""
+    if other.dim() >= 2 and other.size(0) == src.size(0) and other.size(1) == 1:
+        return other.squeeze(1)[src.storage.row()]
+    if other.dim() >= 2 and other.size(0) == 1 and other.size(1) == src.size(1):
+        return other.squeeze(0)[src.storage.col()]
+    raise ValueError(f"Size mismatch: Expected size ({src.size(0)}, 1, ...) or (1, {src.size(1)}, ...), "
+                     f"but got size {other.size()}.")
+
+
+def add(src: SparseTensor, other) -> SparseTensor:
+    """sparse + dense row/column vector (values shifted per row / column; a value-less tensor counts as ones) or
+    sparse + sparse (concatenate + native coalesce with sum) — torch_sparse/add.py:21-56."""
+    if isinstance(other, Tensor):
+        term = _broadcast_to_nnz(src, other)
+        value = src.storage.value()
+        value = term + 1 if value is None else term.to(value.dtype) + value
+        return src.set_value(value, layout="coo")
     if not isinstance(other, SparseTensor):
-        raise NotImplementedError("only SparseTensor + SparseTensor is on the sparse-matmul path")
+        raise NotImplementedError
     rowA, colA, valueA = src.coo()
     rowB, colB, valueB = other.coo()
     value: Optional[Tensor] = None
@@ -36,8 +55,30 @@ def add(src: SparseTensor, other: SparseTensor) -> SparseTensor:
     return SparseTensor(row=row, col=col, value=value, sparse_sizes=(M, N), is_sorted=True, trust_data=True)
 
 
+def add_(src: SparseTensor, other: Tensor) -> SparseTensor:
+    term = _broadcast_to_nnz(src, other)
+    value = src.storage.value()
+    value = term + 1 if value is None else value.add_(term.to(value.dtype))
+    return src.set_value_(value, layout="coo")
+
+
+def add_nnz(src: SparseTensor, other: Tensor, layout: Optional[str] = None) -> SparseTensor:
+    value = src.storage.value()
+    return src.set_value(other.add(1) if value is None else value.add(other.to(value.dtype)), layout=layout)
+
+
+def add_nnz_(src: SparseTensor, other: Tensor, layout: Optional[str] = None) -> SparseTensor:
+    value = src.storage.value()
+    return src.set_value_(other.add(1) if value is None else value.add_(other.to(value.dtype)), layout=layout)
+
+
 SparseTensor.add = lambda self, other: add(self, other)
-SparseTensor.__add__ = lambda self, other: add(self, other)
+SparseTensor.add_ = lambda self, other: add_(self, other)
+SparseTensor.add_nnz = lambda self, other, layout=None: add_nnz(self, other, layout)
+SparseTensor.add_nnz_ = lambda self, other, layout=None: add_nnz_(self, other, layout)
+SparseTensor.__add__ = SparseTensor.add
+SparseTensor.__radd__ = SparseTensor.add
+SparseTensor.__iadd__ = SparseTensor.add_
 
 
 def narrow(src: SparseTensor, dim: int, start: int, length: int) -> SparseTensor:
@@ -79,23 +120,60 @@ def narrow(src: SparseTensor, dim: int, start: int, length: int) -> SparseTensor
 SparseTensor.narrow = lambda self, dim, start, length: narrow(self, dim, start, length)
 
 
-def mul(src: SparseTensor, other: Tensor) -> SparseTensor:
+def mul(src: SparseTensor, other) -> SparseTensor:
     """Scale the stored values row-wise (`other` of shape [M, 1]) or column-wise ([1, N]) — the GCN
-    normalisation step either side of SpMM (torch_sparse/mul.py:22-40, dense-operand branch). A pure
-    gather-multiply on the values; structure and caches are shared with `src`."""
-    if not isinstance(other, Tensor):
-        raise NotImplementedError("sparse * sparse is not on the sparse-matmul path")
-    row, col, value = src.coo()
-    if other.dim() >= 2 and other.size(0) == src.size(0) and other.size(1) == 1:
-        factor = other.squeeze(1)[row]
-    elif other.dim() >= 2 and other.size(0) == 1 and other.size(1) == src.size(1):
-        factor = other.squeeze(0)[col]
+    normalisation step either side of SpMM — or multiply two coalesced SparseTensors entry-wise (the result
+    keeps the positions stored in BOTH operands): torch_sparse/mul.py:22-79. Structure and caches of the
+    dense-operand branch are shared with `src`."""
+    if isinstance(other, Tensor):
+        factor = _broadcast_to_nnz(src, other)
+        value = src.storage.value()
+        return src.set_value(factor if value is None else factor.to(value.dtype) * value, layout="coo")
+    if not isinstance(other, SparseTensor):
+        raise NotImplementedError
+    if not src.is_coalesced():
+        raise ValueError("The `src` tensor is not coalesced")
+    if not other.is_coalesced():
+        raise ValueError("The `other` tensor is not coalesced")
+    rowA, colA, valueA = src.coo()
+    rowB, colB, valueB = other.coo()
+    if valueA is None or valueB is None:
+        raise ValueError("Both sparse tensors must contain values")
+    M, N = max(src.size(0), other.size(0)), max(src.size(1), other.size(1))
+    row, col, value = torch.cat([rowA, rowB]), torch.cat([colA, colB]), torch.cat([valueA, valueB], dim=0)
+    # native stable (row, col) sort of the concatenation: a position stored in both operands shows up as two
+    # neighbours, A's entry first
+    perm = ops.sort_perm(row, col, M, N)
+    if perm is not None:
+        row, col, value = row[perm], col[perm], value[perm]
+    if row.numel() < 2:
+        both = torch.zeros(0, dtype=torch.long, device=row.device)
     else:
-        raise ValueError(f"Size mismatch: Expected size ({src.size(0)}, 1, ...) or (1, {src.size(1)}, ...), "
-                         f"but got size {tuple(other.size())}.")
-    value = factor if value is None else factor.to(value.dtype) * value
-    return src.set_value(value, layout="coo")
+        both = ((row[1:] == row[:-1]) & (col[1:] == col[:-1])).nonzero().view(-1) + 1
+    return SparseTensor(row=row[both], col=col[both], value=value[both - 1] * value[both], sparse_sizes=(M, N),
+                        is_sorted=True, trust_data=True)
+
+
+def mul_(src: SparseTensor, other: Tensor) -> SparseTensor:
+    factor = _broadcast_to_nnz(src, other)
+    value = src.storage.value()
+    return src.set_value_(factor if value is None else value.mul_(factor.to(value.dtype)), layout="coo")
+
+
+def mul_nnz(src: SparseTensor, other: Tensor, layout: Optional[str] = None) -> SparseTensor:
+    value = src.storage.value()
+    return src.set_value(other if value is None else value.mul(other.to(value.dtype)), layout=layout)
+
+
+def mul_nnz_(src: SparseTensor, other: Tensor, layout: Optional[str] = None) -> SparseTensor:
+    value = src.storage.value()
+    return src.set_value_(other if value is None else value.mul_(other.to(value.dtype)), layout=layout)
 
 
 SparseTensor.mul = lambda self, other: mul(self, other)
-SparseTensor.__mul__ = lambda self, other: mul(self, other)
+SparseTensor.mul_ = lambda self, other: mul_(self, other)
+SparseTensor.mul_nnz = lambda self, other, layout=None: mul_nnz(self, other, layout)
+SparseTensor.mul_nnz_ = lambda self, other, layout=None: mul_nnz_(self, other, layout)
+SparseTensor.__mul__ = SparseTensor.mul
+SparseTensor.__rmul__ = SparseTensor.mul
+SparseTensor.__imul__ = SparseTensor.mul_

@@ -151,7 +151,7 @@ static CoLayout co_layout(int64_t E) {
 
 static inline int cgrid(int64_t n) {
   int64_t b = (n + 255) / 256;
-  const int64_t cap = (int64_t)kNumSMs * 32;
+  const int64_t cap = (int64_t)num_sms() * 32;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <limits>
 #include <type_traits>
 
@@ -25,7 +26,20 @@
 
 namespace tsb {
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kDefaultSMs = 148;  // B200: 2 dies x 74 SMs (used only if the attribute query fails)
+constexpr int kMaxDevices = 64;
+
+// SM count of the CURRENT device, queried once per device and cached (thread-safe: idempotent atomic stores).
+static inline int num_sms() {
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return kDefaultSMs;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v < 1) v = kDefaultSMs;
+  cache[dev].store(v, std::memory_order_relaxed);
+  return v;
+}
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

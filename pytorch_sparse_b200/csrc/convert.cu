@@ -167,7 +167,7 @@ segment_reduce_bw_kernel(const int64_t* __restrict__ seg, const int64_t* __restr
 
 static inline int grid1d(int64_t n, int threads) {
   int64_t b = (n + threads - 1) / threads;
-  const int64_t cap = (int64_t)kNumSMs * 32;
+  const int64_t cap = (int64_t)num_sms() * 32;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;

@@ -14,9 +14,10 @@
 
 namespace tsb {
 
+// One staging context PER DEVICE (streams, events and the device staging buffer belong to the device they were
+// created on; callers on different devices run concurrently, callers on the same device serialise on `mu`).
 struct HostCtx {
   std::mutex mu;
-  int device = -1;
   char* buf = nullptr;
   size_t cap = 0;
   cudaStream_t s_up[2] = {nullptr, nullptr}, s_comp = nullptr, s_down = nullptr;
@@ -24,13 +25,45 @@ struct HostCtx {
   cudaEvent_t ev_up[kMaxChunks] = {}, ev_comp[kMaxChunks] = {}, ev_mat[2] = {}, ev_rowptr = nullptr;
   bool init = false;
 };
-static HostCtx g_host;
+static HostCtx g_host[kMaxDevices];
+
+// Drain the four staging streams: on an error path the caller's host buffers and the shared device buffer must not
+// be touched by copies still in flight after the call has returned.
+static void host_drain(HostCtx& c) {
+  if (!c.init) return;
+  for (cudaStream_t s : {c.s_up[0], c.s_up[1], c.s_comp, c.s_down})
+    if (s) cudaStreamSynchronize(s);
+}
+
+static int host_init(HostCtx& c) {
+  if (c.init) return 0;
+  for (int i = 0; i < 2; i++) {
+    TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_up[i], cudaStreamNonBlocking));
+    TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_mat[i], cudaEventDisableTiming));
+  }
+  TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_comp, cudaStreamNonBlocking));
+  TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_down, cudaStreamNonBlocking));
+  TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_rowptr, cudaEventDisableTiming));
+  for (int i = 0; i < HostCtx::kMaxChunks; i++) {
+    TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_up[i], cudaEventDisableTiming));
+    TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_comp[i], cudaEventDisableTiming));
+  }
+  c.init = true;
+  return 0;
+}
 
 }  // namespace tsb
 
 using namespace tsb;
 
 extern "C" int tsb200_version(void) { return TSB200_VERSION; }
+
+// CUDA toolkit the library was compiled with, in CUDA_VERSION encoding (12090 = 12.9) — what the reference's
+// torch.ops.torch_sparse.cuda_version() returns (csrc/version.cpp:27-41) and its import-time check compares with
+// torch.version.cuda (torch_sparse/__init__.py:23-37).
+extern "C" int tsb200_cuda_version(void) { return CUDART_VERSION; }
+
+extern "C" int tsb200_sm_count(void) { return num_sms(); }
 
 extern "C" const char* tsb200_strerror(int code) {
   switch (code) {
@@ -53,6 +86,10 @@ extern "C" int tsb200_device_ok(void) {
   return major == 10 ? 0 : TSB200_ERR_NO_DEVICE;
 }
 
+static int spmm_fw_host_locked(HostCtx& c, const int64_t* rowptr_host, const int64_t* col_host,
+                               const void* value_host, const void* mat_host, void* out_host, int64_t* arg_out_host,
+                               int64_t B, int64_t M, int64_t N, int64_t K, int64_t E, int dtype, int reduce);
+
 extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* col_host, const void* value_host,
                                    const void* mat_host, void* out_host, int64_t* arg_out_host, int64_t B,
                                    int64_t M, int64_t N, int64_t K, int64_t E, int dtype, int reduce) {
@@ -66,24 +103,24 @@ extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* co
   if (E > 0 && (!col_host || !mat_host)) return TSB200_ERR_INVALID_ARG;
   if (int rc = tsb200_device_ok()) return rc;
 
-  HostCtx& c = g_host;
-  std::lock_guard<std::mutex> lock(c.mu);
   int dev = 0;
   TSB_CUDA_TRY(cudaGetDevice(&dev));
-  if (!c.init || c.device != dev) {
-    for (int i = 0; i < 2; i++) {
-      TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_up[i], cudaStreamNonBlocking));
-      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_mat[i], cudaEventDisableTiming));
-    }
-    TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_comp, cudaStreamNonBlocking));
-    TSB_CUDA_TRY(cudaStreamCreateWithFlags(&c.s_down, cudaStreamNonBlocking));
-    TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_rowptr, cudaEventDisableTiming));
-    for (int i = 0; i < HostCtx::kMaxChunks; i++) {
-      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_up[i], cudaEventDisableTiming));
-      TSB_CUDA_TRY(cudaEventCreateWithFlags(&c.ev_comp[i], cudaEventDisableTiming));
-    }
-    c.buf = nullptr; c.cap = 0; c.device = dev; c.init = true;
-  }
+  if (dev < 0 || dev >= kMaxDevices) return TSB200_ERR_NO_DEVICE;
+  HostCtx& c = g_host[dev];
+  std::lock_guard<std::mutex> lock(c.mu);
+  int rc = host_init(c);
+  if (!rc)
+    rc = spmm_fw_host_locked(c, rowptr_host, col_host, value_host, mat_host, out_host, arg_out_host, B, M, N, K, E,
+                             dtype, reduce);
+  if (rc) host_drain(c);  // nothing of this call may still be in flight when the error is returned
+  return rc;
+}
+
+static int spmm_fw_host_locked(HostCtx& c, const int64_t* rowptr_host, const int64_t* col_host,
+                               const void* value_host, const void* mat_host, void* out_host, int64_t* arg_out_host,
+                               int64_t B, int64_t M, int64_t N, int64_t K, int64_t E, int dtype, int reduce) {
+  const size_t es = dtype_size(dtype);
+  const bool arg = reduce == TSB200_MIN || reduce == TSB200_MAX;
   // device layout
   const size_t ws_bytes = tsb200_spmm_fw_workspace_bytes(B, M, K, E, dtype, reduce);
   size_t off = 0;
@@ -95,6 +132,7 @@ extern "C" int tsb200_spmm_fw_host(const int64_t* rowptr_host, const int64_t* co
   const size_t o_arg = off; off += arg ? align_up((size_t)B * M * K * 8, 256) : 0;
   const size_t o_ws = off; off += align_up(ws_bytes, 256);
   if (off > c.cap) {
+    host_drain(c);
     if (c.buf) TSB_CUDA_TRY(cudaFree(c.buf));
     c.buf = nullptr; c.cap = 0;
     TSB_CUDA_TRY(cudaMalloc(&c.buf, off));

@@ -375,9 +375,9 @@ template <typename T, int LPR, int CH, int U, int MINB>
 static int launch_sddmm(SpmmParams p, const void* grad, void* out, cudaStream_t st) {
   auto* kmain = sddmm_vec_kernel<T, LPR, CH, U, MINB>;
   auto* kseg = sddmm_seg_kernel<T, LPR, CH, U, MINB>;
-  static int grid_main = 0, grid_seg = 0;
-  if (!grid_main) grid_main = grid_for((const void*)kmain, kWarpsPerCta * 32);
-  if (!grid_seg) grid_seg = grid_for((const void*)kseg, kWarpsPerCta * 32);
+  static GridCache gc_main, gc_seg;  // per instantiation, per device
+  const int grid_main = gc_main.get((const void*)kmain, kWarpsPerCta * 32);
+  const int grid_seg = gc_seg.get((const void*)kseg, kWarpsPerCta * 32);
   int64_t want = p.M / ((int64_t)grid_main * kWarpsPerCta * 2);
   p.item_shift = 0;
   while (p.item_shift < 5 && ((int64_t)2 << p.item_shift) <= want) p.item_shift++;
@@ -471,7 +471,7 @@ static int launch_value_vec(const int64_t* row, const int64_t* rowptr, const int
                             const void* grad, void* out, int64_t B, int64_t M, int64_t N, int64_t K,
                             int64_t E, bool mean, cudaStream_t st) {
   int64_t blocks = (E + 255) / 256;  // 8 warps x 32 nnz per CTA pass
-  const int64_t cap = (int64_t)kNumSMs * 6;  // 3 resident CTAs/SM, 2 passes
+  const int64_t cap = (int64_t)num_sms() * 6;  // 3 resident CTAs/SM, 2 passes
   if (blocks > cap) blocks = cap;
   value_bw_vec_kernel<T, LPR, U><<<(int)blocks, 256, 0, st>>>(row, rowptr, col, (const T*)mat, (const T*)grad,
                                                              (T*)out, B, M, N, K, E, mean);
@@ -554,7 +554,7 @@ extern "C" int tsb200_spmm_value_bw(const int64_t* row, const int64_t* rowptr, c
   return dispatch_dtype(dtype, [&](auto tag) -> int {
     using T = decltype(tag);
     int64_t blocks = (E + 7) / 8;
-    const int64_t cap = (int64_t)kNumSMs * 32;
+    const int64_t cap = (int64_t)num_sms() * 32;
     if (blocks > cap) blocks = cap;
     value_bw_generic_kernel<T><<<(int)blocks, 256, 0, st>>>(row, rowptr, col, (const T*)mat, (const T*)grad,
                                                            (T*)out, B, M, N, K, E, mean);
@@ -596,7 +596,7 @@ extern "C" int tsb200_spmm_minmax_bw(const int64_t* col, const void* value, cons
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)minmax_bw_kernel<T, A>, 256, 0);
     if (per_sm < 1) per_sm = 1;
     int64_t blocks = ((B * M << lsl) + 255) / 256;
-    const int64_t cap = (int64_t)kNumSMs * per_sm;
+    const int64_t cap = (int64_t)num_sms() * per_sm;
     if (blocks > cap) blocks = cap;
     minmax_bw_kernel<T, A><<<(int)blocks, 256, 0, st>>>(col, (const T*)value, (const T*)mat, (const T*)grad_out,
                                                        arg_out, (A*)grad_value, (A*)grad_mat, B, M, N, K, E, lsl);

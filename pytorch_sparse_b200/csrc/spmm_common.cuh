@@ -244,9 +244,23 @@ static inline int grid_for(const void* kernel, int threads) {
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  int dev = 0, sms = kNumSMs;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return per_sm * sms;
+  return per_sm * num_sms();
 }
+
+// Persistent-grid size of one kernel instantiation, cached PER DEVICE (the occupancy query costs microseconds per
+// launch otherwise). Lock-free: racing threads compute the same value.
+struct GridCache {
+  std::atomic<int> v[kMaxDevices];
+  int get(const void* kernel, int threads) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return grid_for(kernel, threads);
+    int g = v[dev].load(std::memory_order_relaxed);
+    if (g <= 0) {
+      g = grid_for(kernel, threads);
+      v[dev].store(g, std::memory_order_relaxed);
+    }
+    return g;
+  }
+};
 
 }  // namespace tsb

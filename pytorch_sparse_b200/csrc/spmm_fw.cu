@@ -802,9 +802,9 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
   else kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB>;
   constexpr int USEG = (U > LPR) ? LPR : U;  // the row engine needs U * (32 / LPR) <= 32
   auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, USEG, MINB>;
-  static int grid_main = 0, grid_seg = 0;  // per-instantiation cache
-  if (!grid_main) grid_main = grid_for((const void*)kmain, kWarpsPerCta * 32);
-  if (!grid_seg) grid_seg = grid_for((const void*)kseg, kWarpsPerCta * 32);
+  static GridCache gc_main, gc_seg;  // per instantiation, per device
+  const int grid_main = gc_main.get((const void*)kmain, kWarpsPerCta * 32);
+  const int grid_seg = gc_seg.get((const void*)kseg, kWarpsPerCta * 32);
   // small matrices: shrink the work item so that every resident warp gets rows
   int64_t want = p.M * p.B / ((int64_t)grid_main * kWarpsPerCta * 2);
   p.item_shift = 0;
@@ -818,7 +818,7 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
     TSB_LAUNCH_CHECK();
     kseg<<<grid_seg, kWarpsPerCta * 32, 0, st>>>(p);
     TSB_LAUNCH_CHECK();
-    spmm_combine_kernel<T, RED><<<kNumSMs * 2, 128, 0, st>>>(p, kcols);
+    spmm_combine_kernel<T, RED><<<num_sms() * 2, 128, 0, st>>>(p, kcols);
     TSB_LAUNCH_CHECK();
   }
   return 0;
@@ -862,7 +862,7 @@ static int launch_generic(const int64_t* rowptr, const int64_t* col, const void*
                           int64_t E, bool mean, cudaStream_t st) {
   const int64_t warps = B * M;
   int64_t blocks = (warps + 7) / 8;
-  if (blocks > (int64_t)kNumSMs * 64) blocks = (int64_t)kNumSMs * 64;
+  if (blocks > (int64_t)num_sms() * 64) blocks = (int64_t)num_sms() * 64;
   if (blocks < 1) blocks = 1;
   spmm_generic_kernel<T, RED><<<(int)blocks, 256, 0, st>>>(rowptr, col, (const T*)value, (const T*)mat,
                                                            (T*)out, arg_out, B, M, N, K, E, mean);

@@ -539,9 +539,7 @@ template <bool NUMERIC, typename T> static int sp_launch(const SpParams& p, cuda
   int per_sm = 1;
   TSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, kSpThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  int dev = 0, sms = kNumSMs;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int64_t grid = (int64_t)per_sm * sms;
+  int64_t grid = (int64_t)per_sm * num_sms();
   const int64_t grabs = (p.M + kRowsPerGrab - 1) / kRowsPerGrab;
   if (grid > grabs) grid = grabs;
   if (grid < 1) grid = 1;

@@ -84,6 +84,65 @@ def to_symmetric(src: SparseTensor, reduce: str = "sum") -> SparseTensor:
     return SparseTensor(row=r2, col=c2, value=v2, sparse_sizes=(N, N), is_sorted=True, trust_data=True)
 
 
+def masked_select(src: SparseTensor, dim: int, mask: Tensor) -> SparseTensor:
+    """Keep the slices of dimension `dim` where `mask` is set (torch_sparse/masked_select.py: same as an
+    index_select with the set positions)."""
+    return index_select(src, dim, mask.nonzero().view(-1))
+
+
+def select(src: SparseTensor, dim: int, idx: int) -> SparseTensor:
+    """One slice of dimension `dim`, kept as a length-1 dimension (torch_sparse/select.py:4-5)."""
+    return src.narrow(dim, idx, 1)
+
+
+def _getitem(self: SparseTensor, index) -> SparseTensor:
+    """`mat[rows, cols]` with ints, slices, index / bool tensors, lists, numpy arrays and one Ellipsis
+    (torch_sparse/tensor.py:624-671): each item is a narrow / index_select / masked_select on the next dimension."""
+    items = list(index) if isinstance(index, tuple) else [index]
+
+    def is_ellipsis(i):
+        return i is Ellipsis
+
+    if sum(1 for i in items if is_ellipsis(i)) > 1:
+        raise SyntaxError
+    dim, out = 0, self
+    while items:
+        item = items.pop(0)
+        if isinstance(item, (list, tuple)):
+            item = torch.tensor(item, device=self.device())
+        elif type(item).__module__ == "numpy" and hasattr(item, "dtype"):
+            item = torch.from_numpy(item).to(self.device())
+        if isinstance(item, int) and not isinstance(item, bool):
+            out = select(out, dim, item)
+            dim += 1
+        elif isinstance(item, slice):
+            if item.step is not None:
+                raise ValueError("Step parameter not yet supported.")
+            start = 0 if item.start is None else item.start
+            start = self.size(dim) + start if start < 0 else start
+            stop = self.size(dim) if item.stop is None else item.stop
+            stop = self.size(dim) + stop if stop < 0 else stop
+            out = out.narrow(dim, start, max(stop - start, 0))
+            dim += 1
+        elif torch.is_tensor(item):
+            if item.dtype == torch.bool:
+                out = masked_select(out, dim, item)
+                dim += 1
+            elif item.dtype == torch.long:
+                out = index_select(out, dim, item)
+                dim += 1
+        elif is_ellipsis(item):
+            if self.dim() - len(items) < dim:
+                raise SyntaxError
+            dim = self.dim() - len(items)
+        else:
+            raise SyntaxError
+    return out
+
+
+SparseTensor.masked_select = lambda self, dim, mask: masked_select(self, dim, mask)
+SparseTensor.select = lambda self, dim, idx: select(self, dim, idx)
+SparseTensor.__getitem__ = _getitem
 SparseTensor.index_select = lambda self, dim, idx: index_select(self, dim, idx)
 SparseTensor.index_select_nnz = lambda self, idx, layout=None: index_select_nnz(self, idx, layout)
 SparseTensor.to_symmetric = lambda self, reduce="sum": to_symmetric(self, reduce)

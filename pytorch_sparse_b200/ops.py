@@ -672,4 +672,6 @@ def spmm_max(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor) 
 
 
 def cuda_version() -> int:
-    return _lib.lib.tsb200_version()
+    """CUDA toolkit version of the native library in CUDA_VERSION encoding, like
+    torch.ops.torch_sparse.cuda_version() (csrc/version.cpp:27-41)."""
+    return _lib.lib.tsb200_cuda_version()

@@ -195,6 +195,22 @@ class SparseStorage:
         return self._replace(rowptr=rowptr, rowcount=rowcount, colptr=colptr, colcount=colcount,
                              sparse_sizes=tuple(sparse_sizes))
 
+    def sparse_reshape(self, num_rows: int, num_cols: int) -> "SparseStorage":
+        """Same entries, re-indexed for a (num_rows x num_cols) shape with the same element count; -1 infers one
+        extent (torch_sparse/storage.py:316-346). Row-major order is preserved by construction."""
+        assert num_rows > 0 or num_rows == -1
+        assert num_cols > 0 or num_cols == -1
+        assert num_rows > 0 or num_cols > 0
+        total = self._sparse_sizes[0] * self._sparse_sizes[1]
+        if num_rows == -1:
+            num_rows = total // num_cols
+        if num_cols == -1:
+            num_cols = total // num_rows
+        assert num_rows * num_cols == total
+        lin = self._sparse_sizes[1] * self.row() + self._col
+        return SparseStorage(row=torch.div(lin, num_cols, rounding_mode="floor"), col=lin % num_cols,
+                             value=self._value, sparse_sizes=(num_rows, num_cols), is_sorted=True, trust_data=True)
+
     # ------------------------------------------------------------------ derived caches
     def has_rowcount(self) -> bool:
         return self._rowcount is not None

@@ -93,6 +93,10 @@ class SparseTensor:
     def set_value(self, value: Optional[Tensor], layout: Optional[str] = None) -> "SparseTensor":
         return self.from_storage(self.storage.set_value(value, layout))
 
+    def fill_value_(self, fill_value: float, dtype: Optional[torch.dtype] = None) -> "SparseTensor":
+        value = torch.full((self.nnz(),), fill_value, dtype=dtype, device=self.device())
+        return self.set_value_(value, layout="coo")
+
     def fill_value(self, fill_value: float, dtype: Optional[torch.dtype] = None) -> "SparseTensor":
         value = torch.full((self.nnz(),), fill_value, dtype=dtype, device=self.device())
         return self.set_value(value, layout="coo")
@@ -106,6 +110,9 @@ class SparseTensor:
 
     def sparse_resize(self, sparse_sizes: Tuple[int, int]) -> "SparseTensor":
         return self.from_storage(self.storage.sparse_resize(sparse_sizes))
+
+    def sparse_reshape(self, num_rows: int, num_cols: int) -> "SparseTensor":
+        return self.from_storage(self.storage.sparse_reshape(num_rows, num_cols))
 
     def sizes(self) -> List[int]:
         sizes = list(self.sparse_sizes())
@@ -142,6 +149,34 @@ class SparseTensor:
 
     def is_quadratic(self) -> bool:
         return self.sparse_size(0) == self.sparse_size(1)
+
+    def is_symmetric(self) -> bool:
+        """CSR view == CSC view, structure and values (torch_sparse/tensor.py:389-402)."""
+        if not self.is_quadratic():
+            return False
+        rowptr, col, value1 = self.csr()
+        colptr, row, value2 = self.csc()
+        if bool((rowptr != colptr).any()) or bool((col != row).any()):
+            return False
+        if value1 is None or value2 is None:
+            return True
+        return bool((value1 == value2).all())
+
+    def __eq__(self, other) -> bool:
+        """Same sizes, same CSR structure, same values (torch_sparse/tensor.py:293-313)."""
+        if not isinstance(other, self.__class__):
+            return False
+        if self.sizes() != other.sizes():
+            return False
+        rowptrA, colA, valueA = self.csr()
+        rowptrB, colB, valueB = other.csr()
+        if (valueA is None) != (valueB is None):
+            return False
+        if not torch.equal(rowptrA, rowptrB) or not torch.equal(colA, colB):
+            return False
+        return True if valueA is None else torch.equal(valueA, valueB)
+
+    __hash__ = object.__hash__
 
     # ------------------------------------------------------------------ coalesce / caches
     def is_coalesced(self) -> bool:

@@ -3,12 +3,14 @@
 
     torch.ops.tsb200.{spmm_sum, spmm_mean, spmm_min, spmm_max, ind2ptr, ptr2ind, cuda_version}
 
-and, unless TSB200_REGISTER_TORCH_SPARSE=0 or a real torch_sparse build already owns the namespace,
+and — unless a `torch_sparse` package is importable in this environment or TSB200_REGISTER_TORCH_SPARSE=0 —
 the same operators as `torch.ops.torch_sparse.*`, so code that calls the reference's ops by name
-keeps working on top of this package.
+(including TorchScript code: `torch.jit.script` functions can call these ops) keeps working on top of this package.
 """
 from __future__ import annotations
 
+import importlib.util
+import logging
 import os
 
 import torch
@@ -31,21 +33,40 @@ _IMPLS = {
     "ind2ptr": ops.ind2ptr, "ptr2ind": ops.ptr2ind, "cuda_version": ops.cuda_version,
 }
 _LIBS = []  # keep Library objects alive
+log = logging.getLogger(__name__)
 
 
 def _register(ns: str) -> bool:
+    """All-or-nothing: if any definition collides (a compiled torch_sparse already owns the namespace) the partial
+    fragment is destroyed again, so the namespace is never left half registered."""
+    lib = torch.library.Library(ns, "FRAGMENT")
     try:
-        lib = torch.library.Library(ns, "FRAGMENT")
         for name, schema in _SCHEMAS.items():
             lib.define(name + schema)
             # the Python implementations wrap autograd.Functions, i.e. they are "composite implicit"
             lib.impl(name, _IMPLS[name], "CompositeImplicitAutograd")
-    except Exception:  # namespace already owned by a compiled torch_sparse
+    except Exception as e:
+        lib._destroy()
+        log.warning("pytorch_sparse_b200: torch.ops.%s.* not registered (%s)", ns, e)
         return False
     _LIBS.append(lib)
     return True
 
 
+def _real_torch_sparse_present() -> bool:
+    try:
+        spec = importlib.util.find_spec("torch_sparse")
+    except (ImportError, ValueError):
+        return False
+    return spec is not None
+
+
 REGISTERED = {"tsb200": _register("tsb200")}
-if os.environ.get("TSB200_REGISTER_TORCH_SPARSE", "1") != "0":
+# Aliasing into the reference's own namespace: on by default only when no `torch_sparse` package is importable
+# (importing a compiled torch_sparse afterwards would collide with these definitions). TSB200_REGISTER_TORCH_SPARSE=1
+# forces it (the reference-suite shim does), =0 forbids it.
+_want = os.environ.get("TSB200_REGISTER_TORCH_SPARSE")
+if _want == "1" or (_want is None and not _real_torch_sparse_present()):
     REGISTERED["torch_sparse"] = _register("torch_sparse")
+else:
+    REGISTERED["torch_sparse"] = False

@@ -101,3 +101,27 @@ def test_host_buffer_spmm_chunked_pipeline():
         assert torch.equal(out, ref.cpu()), red
         if arg is not None:
             assert torch.equal(arg, ref_arg.cpu()), red
+
+
+def test_torchscript_function_over_registered_ops():
+    """A TorchScript function calling the registered ops computes the same as the Python API
+    (the reference's scripted classes call torch.ops.torch_sparse.* the same way, storage.py:193,209,376)."""
+    from typing import Optional
+
+    @torch.jit.script
+    def scripted(rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], x: torch.Tensor):
+        row = torch.ops.torch_sparse.ptr2ind(rowptr, col.numel())
+        out = torch.ops.torch_sparse.spmm_sum(row, rowptr, col, value, None, None, x)
+        mx, arg = torch.ops.torch_sparse.spmm_max(rowptr, col, value, x)
+        return row, out, mx, arg
+
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 40, 30, 16
+    dense = torch.randn(M, N, generator=g) * (torch.rand(M, N, generator=g) < 0.2)
+    a = ts.SparseTensor.from_dense(dense.to("cuda:0"))
+    x = torch.randn(N, K, generator=g).to("cuda:0")
+    rowptr, col, value = a.csr()
+    row, out, mx, arg = scripted(rowptr, col, value, x)
+    assert torch.equal(row, a.storage.row())
+    assert torch.allclose(out, dense.to("cuda:0") @ x, atol=1e-5)
+    assert torch.equal(mx, ts.matmul(a, x, "max"))

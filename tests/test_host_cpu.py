@@ -232,3 +232,31 @@ def test_index_select_host_bookkeeping_matches_reference():
             for lay in ("coo", "csc"):
                 sn, ref = a.index_select_nnz(i["idxe"], lay), case[f"selnnz_{lay}_{tag}"]
                 assert torch.equal(sn.storage.row(), ref["row"]) and torch.equal(sn.storage.col(), ref["col"])
+
+
+def test_torchscript_functions_can_call_the_registered_ops():
+    """The reference's Python layer is TorchScript that calls torch.ops.torch_sparse.* (storage.py:193,209,376);
+    the same works on the operators this package registers: scripting succeeds and the call reaches the op
+    (which rejects CPU tensors — there is no CPU path)."""
+    from typing import Optional
+
+    import torch
+    import pytorch_sparse_b200  # noqa: F401
+
+    @torch.jit.script
+    def scripted(rowptr: torch.Tensor, col: torch.Tensor, value: Optional[torch.Tensor], x: torch.Tensor):
+        row = torch.ops.tsb200.ptr2ind(rowptr, col.numel())
+        return torch.ops.tsb200.spmm_sum(row, rowptr, col, value, None, None, x)
+
+    assert "tsb200::spmm_sum" in str(scripted.graph) and "tsb200::ptr2ind" in str(scripted.graph)
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        scripted(torch.tensor([0, 1]), torch.tensor([0]), None, torch.ones(1, 2))
+
+
+def test_cuda_version_op_matches_reference_encoding():
+    import torch
+    import pytorch_sparse_b200  # noqa: F401
+    v = torch.ops.tsb200.cuda_version()
+    # CUDA_VERSION encoding (csrc/version.cpp:27-41); the reference's import check (torch_sparse/__init__.py:23-37)
+    # derives major from the first two digits and must agree with torch's CUDA major
+    assert v >= 12000 and int(str(v)[0:2]) == int(torch.version.cuda.split(".")[0])

@@ -162,3 +162,62 @@ def test_to_symmetric_vs_reference(name):
             assert s.sparse_sizes() == tuple(ref["sizes"])
             for k in ("row", "col", "value"):
                 _same(getattr(s.storage, k)(), ref[k], (name, tag, red, k))
+
+
+@pytest.mark.parametrize("dtype", [torch.half, torch.float, torch.double, torch.int, torch.long, torch.bfloat16])
+def test_add_and_sparse_sparse_mul_reference_cases(dtype):
+    """The assertions of test/test_add.py:12-30 and test/test_mul.py:12-30, 41-57 (those tests end with a
+    @torch.jit.script over SparseTensor arguments, which this package does not provide)."""
+    rowA = torch.tensor([0, 0, 1, 2, 2], device=DEV)
+    colA = torch.tensor([0, 2, 1, 0, 1], device=DEV)
+    A = ts.SparseTensor(row=rowA, col=colA, value=torch.tensor([1, 2, 4, 1, 3], dtype=dtype, device=DEV))
+    rowB = torch.tensor([0, 0, 1, 2, 2], device=DEV)
+    colB = torch.tensor([1, 2, 2, 1, 2], device=DEV)
+    B = ts.SparseTensor(row=rowB, col=colB, value=torch.tensor([2, 3, 1, 2, 4], dtype=dtype, device=DEV))
+    r, c, v = (A + B).coo()
+    assert r.tolist() == [0, 0, 0, 1, 1, 2, 2, 2] and c.tolist() == [0, 1, 2, 1, 2, 0, 1, 2]
+    assert v.tolist() == [1, 2, 5, 4, 1, 1, 5, 4]
+    r, c, v = (A * B).coo()
+    assert r.tolist() == [0, 2] and c.tolist() == [2, 1] and v.tolist() == [6, 6]
+    A1 = ts.SparseTensor(row=torch.tensor([0], device=DEV), col=torch.tensor([1], device=DEV),
+                         value=torch.tensor([1], dtype=dtype, device=DEV))
+    B1 = ts.SparseTensor(row=torch.tensor([1], device=DEV), col=torch.tensor([0], device=DEV),
+                         value=torch.tensor([2], dtype=dtype, device=DEV))
+    r, c, v = (A1 * B1).coo()
+    assert r.tolist() == [] and c.tolist() == [] and v.tolist() == []
+
+
+def test_dense_vector_add_mul_variants_and_getitem():
+    """torch_sparse/add.py:21-37,59-104, mul.py:82-125, tensor.py:624-671 vs dense arithmetic."""
+    g = torch.Generator().manual_seed(5)
+    M, N = 12, 9
+    dense = (torch.randn(M, N, generator=g, dtype=torch.float64) * (torch.rand(M, N, generator=g) < 0.4)).to(DEV)
+    A = ts.SparseTensor.from_dense(dense)
+    mask = (dense != 0).to(dense.dtype)
+    r = torch.randn(M, 1, generator=g, dtype=torch.float64).to(DEV)
+    c = torch.randn(1, N, generator=g, dtype=torch.float64).to(DEV)
+    assert torch.allclose((A + r).to_dense(), (dense + r) * mask) and torch.allclose((c + A).to_dense(), (dense + c) * mask)
+    assert torch.allclose((A * r).to_dense(), dense * r) and torch.allclose((c * A).to_dense(), dense * c)
+    S = ts.SparseTensor.from_dense(dense, has_value=False)
+    assert torch.allclose((S + r).to_dense(), (1 + r) * mask) and torch.allclose((S * c).to_dense(), c * mask)
+    nnzv = torch.randn(A.nnz(), generator=g, dtype=torch.float64).to(DEV)
+    assert torch.allclose(A.mul_nnz(nnzv).storage.value(), A.storage.value() * nnzv)
+    assert torch.allclose(A.add_nnz(nnzv).storage.value(), A.storage.value() + nnzv)
+    B = A.clone()
+    B *= r
+    B += c
+    assert torch.allclose(B.to_dense(), (dense * r + c) * mask)
+    # __getitem__: slices, index / bool tensors, Ellipsis
+    idx = torch.tensor([3, 0, 3, 7], device=DEV)
+    keep = torch.zeros(N, dtype=torch.bool, device=DEV)
+    keep[[1, 4, 8]] = True
+    assert torch.equal(A[2:7, :4].to_dense(), dense[2:7, :4])
+    assert torch.equal(A[idx].to_dense(), dense[idx])
+    assert torch.equal(A[idx, keep].to_dense(), dense[idx][:, keep])
+    assert torch.equal(A[..., 2:5].to_dense(), dense[:, 2:5])
+    assert torch.equal(A[5].to_dense(), dense[5:6])
+    # sparse_reshape / is_symmetric / __eq__
+    assert torch.equal(A.sparse_reshape(6, -1).to_dense(), dense.reshape(6, 18))
+    sym = A[:9, :9].to_symmetric()
+    assert sym.is_symmetric() and not A[:9, :9].is_symmetric()
+    assert A == ts.SparseTensor.from_dense(dense) and A != A.set_value(A.storage.value() + 1, layout="coo")
