@@ -93,6 +93,18 @@ TSB200_API int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
                    int64_t E, int dtype, int reduce, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* One COLUMN BLOCK of a SUM SpMM (multi-GPU pipelining: the dense operand arrives block by block over NVLink and
+ * block p of A's columns is multiplied as soon as block p of `mat` has landed; no counterpart in the reference, which
+ * has no collectives — the partitioner semantics are torch_sparse/narrow.py:15-42). (rowptr, col, value) hold only the
+ * entries of A whose column lies in the block (col still indexes the full `mat`). The launches of one product share
+ * an fp32 `partial` [B, M, K]:  acc_mode 1 = first block (partial = A_p mat), 2 = partial += A_p mat,
+ * 3 = last block: out = cast(partial + A_p mat). F32 / F16 / BF16 with K * sizeof(dtype) % 16 == 0 only; E > 0.
+ * Workspace: tsb200_spmm_fw_workspace_bytes(B, M, K, E, dtype, TSB200_SUM). */
+TSB200_API int tsb200_spmm_fw_acc(const int64_t* rowptr, const int64_t* col, const void* value, const void* mat,
+                                  void* out, float* partial, int acc_mode, int64_t B, int64_t M, int64_t N,
+                                  int64_t K, int64_t E, int dtype, void* workspace, size_t workspace_bytes,
+                                  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * SpMM value gradient (SDDMM).  Replaces spmm_value_bw -> spmm_value_bw_cpu / _cuda
  *   (csrc/spmm.cpp:37-49, csrc/cpu/spmm_cpu.cpp:103-152, csrc/cuda/spmm_cuda.cu:196-237).
@@ -227,6 +239,24 @@ TSB200_API int tsb200_spspmm_numeric(const int64_t* rowptr_a, const int64_t* col
                           int64_t M, int64_t Kd, int64_t N, int64_t nnz_a, int64_t nnz_b,
                           const int64_t* rowptr_c, int64_t* row_c, int64_t* col_c, void* val_c,
                           int dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Single-pass SpSpMM (same contract and preconditions as the two phases above, half the work when the caller can
+ * afford output arrays sized by an UPPER BOUND of nnz(C)):
+ *   tsb200_spspmm_bound: the number of products sum_{e in A} |B row col_a[e]| >= nnz(C), copied asynchronously to
+ *     *bound_host (pinned int64). workspace: the SpSpMM workspace (>= 256 bytes are used).
+ *   tsb200_spspmm_fused: one kernel computes structure and values. Every output row is counted, then placed behind
+ *     the rows before it through a decoupled look-back over per-row status words in the workspace (rows are handed
+ *     out in increasing order to a resident persistent grid), so no symbolic pre-pass is needed. row_c / col_c /
+ *     val_c hold `capacity` entries (capacity >= the bound is always enough); rowptr_c i64[M+1] is written;
+ *     *nnz_c_host (pinned int64) receives nnz(C) asynchronously, or -1 if capacity was too small (nothing is written
+ *     past `capacity`). Entries [nnz(C), capacity) of the arrays stay untouched. */
+TSB200_API int tsb200_spspmm_bound(const int64_t* col_a, const int64_t* rowptr_b, int64_t nnz_a, void* workspace,
+                                   size_t workspace_bytes, int64_t* bound_host, void* stream);
+TSB200_API int tsb200_spspmm_fused(const int64_t* rowptr_a, const int64_t* col_a, const void* val_a,
+                                   const int64_t* rowptr_b, const int64_t* col_b, const void* val_b, int64_t M,
+                                   int64_t Kd, int64_t N, int64_t nnz_a, int64_t nnz_b, int64_t* rowptr_c,
+                                   int64_t* row_c, int64_t* col_c, void* val_c, int64_t capacity, int dtype,
+                                   void* workspace, size_t workspace_bytes, int64_t* nnz_c_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-buffer SpMM (the end-to-end call a reference-side binding makes with CPU tensors):

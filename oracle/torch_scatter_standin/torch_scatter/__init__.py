@@ -47,10 +47,12 @@ def scatter(src: Tensor, index: Tensor, dim: int = -1, out: Optional[Tensor] = N
         if src.is_floating_point():
             return res / cnt
         return torch.div(res, cnt, rounding_mode="floor")
+    # min/max come back as fresh tensors: the reference's test edits them in place before calling backward
+    # (test/test_matmul.py:29-32), which torch_scatter's own autograd Function allows
     if reduce == "min":
-        return res.scatter_reduce_(dim, idx, src, "amin", include_self=False)
+        return res.scatter_reduce_(dim, idx, src, "amin", include_self=False).clone()
     if reduce == "max":
-        return res.scatter_reduce_(dim, idx, src, "amax", include_self=False)
+        return res.scatter_reduce_(dim, idx, src, "amax", include_self=False).clone()
     raise ValueError
 
 

@@ -38,6 +38,10 @@ struct SpmmParams {
   int item_shift;  // work item = (1 << item_shift) consecutive rows, <= 32
   int mean;  // SUM kernels: divide by max(count,1) at the end
   int k0;  // first column handled by this launch (column tiling for very wide K)
+  // column-block pipelining (SUM only): the product is built from several launches over disjoint column blocks of
+  // A that share an fp32 partial [B, M, K]:  1 = write the partial, 2 = add to it, 3 = add to it and write `out`
+  float* partial;
+  int acc_mode;
   // workspace
   unsigned int* counters;  // [0] item counter, [1] #segments, [2] #long rows, [3] #partial slots
   Segment* segs;

@@ -158,7 +158,7 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
   // final write of one row (group 0 lanes). count = row degree.
   __device__ __forceinline__ void store_row(T* __restrict__ out_row, int64_t* __restrict__ arg_row,
                                             int64_t count, int64_t E, const bool (&col_ok)[CH], int li,
-                                            bool mean) {
+                                            bool mean, float* __restrict__ part_row = nullptr, int acc_mode = 0) {
 #pragma unroll
     for (int ch = 0; ch < CH; ch++) {
       if (!col_ok[ch]) continue;
@@ -171,6 +171,21 @@ template <typename T, int RED, int LPR, int CH, int U> struct RowEngine {
         f[i] = a;
       }
       const int koff = (ch * LPR + li) * VEC;
+      if (RED == R_SUM && acc_mode) {  // column-block pipelining: fp32 partial shared by the launches of one product
+        float4* pr = reinterpret_cast<float4*>(part_row + koff);
+        if (acc_mode != 1) {
+#pragma unroll
+          for (int i = 0; i < VEC; i += 4) {
+            const float4 q = pr[i >> 2];
+            f[i] += q.x; f[i + 1] += q.y; f[i + 2] += q.z; f[i + 3] += q.w;
+          }
+        }
+        if (acc_mode != 3) {
+#pragma unroll
+          for (int i = 0; i < VEC; i += 4) pr[i >> 2] = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          continue;
+        }
+      }
       stg128_stream(out_row + koff, V::pack(f));
       if (ARG) {
 #pragma unroll
@@ -332,7 +347,8 @@ template <typename T, int RED, int LPR, int CH, int U> struct MinMax16Engine {
   }
 
   __device__ __forceinline__ void store_row(T* __restrict__ out_row, int64_t* __restrict__ arg_row,
-                                            int64_t count, int64_t E, const bool (&col_ok)[CH], int li, bool) {
+                                            int64_t count, int64_t E, const bool (&col_ok)[CH], int li, bool,
+                                            float* = nullptr, int = 0) {
 #pragma unroll
     for (int ch = 0; ch < CH; ch++) {
       if (!col_ok[ch]) continue;
@@ -356,7 +372,7 @@ template <typename T, int RED, int LPR, int CH, int U> struct EngineFor {
                                          RowEngine<T, RED, LPR, CH, U>>::type;
 };
 
-template <typename T, int RED, int LPR, int CH, int U, int MINB>
+template <typename T, int RED, int LPR, int CH, int U, int MINB, bool ACC = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_vec_kernel(const SpmmParams p) {
   using Eng = typename EngineFor<T, RED, LPR, CH, U>::type;
@@ -453,6 +469,7 @@ spmm_vec_kernel(const SpmmParams p) {
     asm volatile("" : "+l"(matb));  // keep the gather base in a register
     T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0;
     int64_t* argb = p.arg_out ? p.arg_out + (b * p.M + r0) * p.K + p.k0 : nullptr;
+    float* partb = ACC ? p.partial + (b * p.M + r0) * p.K + p.k0 : nullptr;
 
     for (int rl = 0; rl < nrows; rl++) {
       if ((defer_mask >> rl) & 1u) continue;
@@ -462,7 +479,8 @@ spmm_vec_kernel(const SpmmParams p) {
       eng.init();
       eng.accumulate(ring, s, e, matb, row_bytes, col_ok, lane, g, pol);
       eng.reduce_groups();
-      if (g == 0) eng.store_row(outb + (int64_t)rl * p.K, argb ? argb + (int64_t)rl * p.K : nullptr, e - s, p.E, col_ok, li, p.mean != 0);
+      if (g == 0) eng.store_row(outb + (int64_t)rl * p.K, argb ? argb + (int64_t)rl * p.K : nullptr, e - s, p.E, col_ok, li, p.mean != 0,
+                                ACC ? partb + (int64_t)rl * p.K : nullptr, ACC ? p.acc_mode : 0);
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
   }
@@ -484,7 +502,7 @@ template <> __device__ __forceinline__ unsigned short load_vraw<__half>(const __
   return __ldg(reinterpret_cast<const unsigned short*>(p));
 }
 
-template <typename T, int RED, int LPR, int U, int MINB>
+template <typename T, int RED, int LPR, int U, int MINB, bool ACC = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_gpr_kernel(const SpmmParams p) {
   using V = Vec<T>;
@@ -565,6 +583,7 @@ spmm_gpr_kernel(const SpmmParams p) {
     const T* __restrict__ valb = has_val ? val + base : nullptr;
     T* outb = (T*)p.out + (b * p.M + r0) * p.K + p.k0;
     int64_t* argb = p.arg_out ? p.arg_out + (b * p.M + r0) * p.K + p.k0 : nullptr;
+    float* partb = ACC ? p.partial + (b * p.M + r0) * p.K + p.k0 : nullptr;
     const bool col_ok_arr[1] = {col_ok};
     const int jbase = (int)base;  // absolute nnz index of ring-relative 0 (E < 2^31)
 
@@ -621,14 +640,14 @@ spmm_gpr_kernel(const SpmmParams p) {
         }
       }
       if (mine) eng.store_row(outb + (int64_t)rl * p.K, argb ? argb + (int64_t)rl * p.K : nullptr, len, p.E, col_ok_arr, li,
-                              p.mean != 0);
+                              p.mean != 0, ACC ? partb + (int64_t)rl * p.K : nullptr, ACC ? p.acc_mode : 0);
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
   }
 }
 
 // one warp per queued segment
-template <typename T, int RED, int LPR, int CH, int U, int MINB>
+template <typename T, int RED, int LPR, int CH, int U, int MINB, bool ACC = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_seg_kernel(const SpmmParams p) {
   using Eng = typename EngineFor<T, RED, LPR, CH, U>::type;
@@ -675,7 +694,8 @@ spmm_seg_kernel(const SpmmParams p) {
       if (S.slot < 0) {
         eng.store_row((T*)p.out + (b * p.M + row) * p.K + p.k0,
                       p.arg_out ? p.arg_out + (b * p.M + row) * p.K + p.k0 : nullptr,
-                      S.end - S.start, p.E, col_ok, li, p.mean != 0);
+                      S.end - S.start, p.E, col_ok, li, p.mean != 0,
+                      ACC ? p.partial + (b * p.M + row) * p.K + p.k0 : nullptr, ACC ? p.acc_mode : 0);
       } else {
         float* pv = (float*)p.part_val + S.slot * p.K + p.k0;
         int64_t* pa = Eng::ARG ? p.part_arg + S.slot * p.K + p.k0 : nullptr;
@@ -719,6 +739,11 @@ __global__ void spmm_combine_kernel(const SpmmParams p, int kcols) {
         }
       }
       if (RED == R_SUM && p.mean) a = a / (float)(count > 0 ? count : 1);
+      if (RED == R_SUM && p.acc_mode) {
+        float* pr = p.partial + L.row_b * p.K + kk;
+        if (p.acc_mode != 1) a += *pr;
+        if (p.acc_mode != 3) { *pr = a; continue; }
+      }
       ((T*)p.out)[L.row_b * p.K + kk] = Traits<T>::from_acc(a);
       if (ARG) p.arg_out[L.row_b * p.K + kk] = ar;
     }
@@ -793,15 +818,15 @@ static bool vec_eligible(int dtype, int64_t K, int64_t E, int64_t N, const void*
   return true;
 }
 
-template <typename T, int RED, int LPR, int CH, int U, int MINB = 1, bool GPR = false>
+template <typename T, int RED, bool ACC, int LPR, int CH, int U, int MINB = 1, bool GPR = false>
 static int launch_vec(SpmmParams p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int kcols = LPR * CH * VEC;
   void (*kmain)(const SpmmParams);
-  if constexpr (GPR) kmain = spmm_gpr_kernel<T, RED, LPR, U, MINB>;
-  else kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB>;
+  if constexpr (GPR) kmain = spmm_gpr_kernel<T, RED, LPR, U, MINB, ACC>;
+  else kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB, ACC>;
   constexpr int USEG = (U > LPR) ? LPR : U;  // the row engine needs U * (32 / LPR) <= 32
-  auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, USEG, MINB>;
+  auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, USEG, MINB, ACC>;
   static GridCache gc_main, gc_seg;  // per instantiation, per device
   const int grid_main = gc_main.get((const void*)kmain, kWarpsPerCta * 32);
   const int grid_seg = gc_seg.get((const void*)kseg, kWarpsPerCta * 32);
@@ -827,22 +852,22 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
 // (LPR, CH) follow from the width of a dense row; (U, MINB) = gathers in flight per lane and CTAs
 // per SM, tuned on B200 (profiles/r01_variant_sweep.txt): the kernel is HBM-latency bound, so
 // resident warps x gathers-in-flight wins; 40 warps/SM x 4 x 16 B per lane saturates HBM.
-template <typename T, int RED> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
+template <typename T, int RED, bool ACC = false> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   const int64_t vecs = p.K / VEC;  // 16-byte vectors per dense row
   {  // narrow rows: group-per-row kernel (all reductions)
-    if (vecs <= 1) return launch_vec<T, RED, 1, 1, 4, 5, true>(p, st);
-    if (vecs <= 2) return launch_vec<T, RED, 2, 1, 4, 5, true>(p, st);
-    if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4, 5, true>(p, st);
-    if (vecs <= 8) return launch_vec<T, RED, 8, 1, 4, 5, true>(p, st);
+    if (vecs <= 1) return launch_vec<T, RED, ACC, 1, 1, 4, 5, true>(p, st);
+    if (vecs <= 2) return launch_vec<T, RED, ACC, 2, 1, 4, 5, true>(p, st);
+    if (vecs <= 4) return launch_vec<T, RED, ACC, 4, 1, 4, 5, true>(p, st);
+    if (vecs <= 8) return launch_vec<T, RED, ACC, 8, 1, 4, 5, true>(p, st);
   }
-  if (vecs <= 1) return launch_vec<T, RED, 1, 1, 1, 6>(p, st);
-  if (vecs <= 4) return launch_vec<T, RED, 4, 1, 4, 5>(p, st);
-  if (vecs <= 8) return launch_vec<T, RED, 8, 1, 4, 5>(p, st);
-  if (vecs <= 16) return launch_vec<T, RED, 16, 1, 4, 5>(p, st);
-  if (vecs <= 32) return launch_vec<T, RED, 32, 1, 4, 5>(p, st);
-  if (vecs <= 64) return launch_vec<T, RED, 32, 2, 4, 3>(p, st);
-  return launch_vec<T, RED, 32, 4, 2, 3>(p, st);  // column-tiled beyond 128 vectors
+  if (vecs <= 1) return launch_vec<T, RED, ACC, 1, 1, 1, 6>(p, st);
+  if (vecs <= 4) return launch_vec<T, RED, ACC, 4, 1, 4, 5>(p, st);
+  if (vecs <= 8) return launch_vec<T, RED, ACC, 8, 1, 4, 5>(p, st);
+  if (vecs <= 16) return launch_vec<T, RED, ACC, 16, 1, 4, 5>(p, st);
+  if (vecs <= 32) return launch_vec<T, RED, ACC, 32, 1, 4, 5>(p, st);
+  if (vecs <= 64) return launch_vec<T, RED, ACC, 32, 2, 4, 3>(p, st);
+  return launch_vec<T, RED, ACC, 32, 4, 2, 3>(p, st);  // column-tiled beyond 128 vectors
 }
 
 template <typename T> static int dispatch_red_vec(SpmmParams p, int reduce, cudaStream_t st) {
@@ -903,6 +928,7 @@ extern "C" int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
     SpmmParams p;
     p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = arg_out;
     p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
+    p.partial = nullptr; p.acc_mode = 0;
     p.counters = (unsigned int*)(ws + L.counters);
     p.segs = (Segment*)(ws + L.segs);
     p.longs = (LongRow*)(ws + L.longs);
@@ -926,4 +952,41 @@ extern "C" int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
     }
     return TSB200_ERR_INVALID_ARG;
   });
+}
+
+// One column block of a SUM SpMM whose blocks are launched separately (the dense operand arrives block by block):
+// same kernels, the row results go through an fp32 partial instead of straight to `out`.
+extern "C" int tsb200_spmm_fw_acc(const int64_t* rowptr, const int64_t* col, const void* value, const void* mat,
+                                  void* out, float* partial, int acc_mode, int64_t B, int64_t M, int64_t N,
+                                  int64_t K, int64_t E, int dtype, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  if (B < 0 || M < 0 || N < 0 || K < 0 || E <= 0) return TSB200_ERR_INVALID_ARG;
+  if (acc_mode < 1 || acc_mode > 3 || !partial || !rowptr || !col || !mat) return TSB200_ERR_INVALID_ARG;
+  if (acc_mode == 3 && !out) return TSB200_ERR_INVALID_ARG;
+  if (B * M * K == 0) return 0;
+  if (((uintptr_t)partial & 15) || (K & 3)) return TSB200_ERR_UNSUPPORTED;
+  // `out` is only dereferenced by the last block; alignment is checked against the partial for the others
+  if (!vec_eligible(dtype, K, E, N, value, mat, acc_mode == 3 ? out : (void*)partial, col, nullptr))
+    return TSB200_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const WsLayout L = ws_layout(B, K, E, false);
+  if (!workspace || workspace_bytes < L.total) return TSB200_ERR_WORKSPACE;
+  if ((uintptr_t)workspace & 255) return TSB200_ERR_INVALID_ARG;
+  char* ws = (char*)workspace;
+  SpmmParams p;
+  p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = nullptr;
+  p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
+  p.partial = partial; p.acc_mode = acc_mode;
+  p.counters = (unsigned int*)(ws + L.counters);
+  p.segs = (Segment*)(ws + L.segs);
+  p.longs = (LongRow*)(ws + L.longs);
+  p.part_val = ws + L.part_val;
+  p.part_arg = nullptr;
+  p.seg_cap = L.seg_cap; p.long_cap = L.long_cap; p.slot_cap = L.slot_cap;
+  switch (dtype) {
+    case TSB200_F32: return dispatch_shape<float, R_SUM, true>(p, st);
+    case TSB200_F16: return dispatch_shape<__half, R_SUM, true>(p, st);
+    case TSB200_BF16: return dispatch_shape<__nv_bfloat16, R_SUM, true>(p, st);
+  }
+  return TSB200_ERR_UNSUPPORTED;
 }

@@ -44,7 +44,6 @@ constexpr int kFlatU = 8;                         // products per thread on the 
 constexpr int kStageCap = kFlatU * kSpThreads;    // output entries staged in shared memory per row (2048)
 constexpr int kMaxWindowLog2 = 18;
 constexpr int kMaxWindowBits = 1 << kMaxWindowLog2;
-constexpr int kRowsPerGrab = 8;                   // rows handed to a CTA per atomic
 constexpr int kABatch = 128;                      // A entries staged per batch
 static_assert(kStageCap <= (1 << (32 - kMaxWindowLog2 - 1)), "owner id and column share one 32-bit word");
 
@@ -56,6 +55,9 @@ struct SpParams {
   const int64_t* rowptr_c;  // numeric
   int64_t* row_c; int64_t* col_c; void* val_c;
   unsigned int* counter;
+  unsigned long long* status;  // FUSED: per-row look-back words (zeroed by the host)
+  int64_t capacity;            // FUSED: entries the output arrays can hold
+  int* overflow;               // FUSED: set when a row would not fit
   int window_bits;  // power of two, 1024 .. 2^18
   int log2_wpt;     // log2(bitmap words per scan chunk), 2..5; chunks = (window_bits/32) >> log2_wpt <= 256
 };
@@ -187,8 +189,53 @@ __device__ __forceinline__ int sp_count_clear_chunk(uint32_t* bitmap, int lw) {
   return cnt;
 }
 
-template <bool NUMERIC, typename T>
-__global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : (NUMERIC ? 4 : 5)) spspmm_kernel(const SpParams p) {
+enum { SP_SYM = 0, SP_NUM = 1, SP_FUSED = 2 };
+
+// ---- single-pass (FUSED) mode: per-row status words for the decoupled look-back ----------------------------
+// status[i] = flag << 62 | value:  flag 0 = row not counted yet, 1 = value is the row's nnz (aggregate),
+// 2 = value is the inclusive prefix (nnz of rows 0..i). One 64-bit word per row, written/read with relaxed
+// gpu-scope accesses: flag and value travel in one word, and no other data is exchanged between CTAs.
+constexpr unsigned long long kStAgg = 1ull << 62, kStPrefix = 2ull << 62, kStMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long sp_ld_status(const unsigned long long* q) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sp_st_status(unsigned long long* q, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
+
+// One warp: number of output entries of all rows < i. Lane l inspects row j - l; a row that has published its
+// inclusive prefix ends the walk. Rows are claimed in increasing order by CTAs that are running, and a row's
+// aggregate depends on no other row, so every predecessor's status eventually becomes non-zero.
+__device__ __forceinline__ int64_t sp_lookback(const unsigned long long* status, int64_t i, int lane) {
+  int64_t excl = 0;
+  for (int64_t j = i - 1; j >= 0; j -= 32) {
+    const int64_t r = j - lane;
+    unsigned long long st = kStPrefix;  // rows before row 0: inclusive prefix 0
+    if (r >= 0) {
+      st = sp_ld_status(status + r);
+      while ((st >> 62) == 0) {
+        __nanosleep(40);
+        st = sp_ld_status(status + r);
+      }
+    }
+    const unsigned pm = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+    long long v = (long long)(st & kStMask);
+    if (pm && lane > __ffs(pm) - 1) v = 0;  // rows older than the nearest published prefix are inside it
+#pragma unroll
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    excl += v;
+    if (pm) break;
+  }
+  return excl;
+}
+
+template <int MODE, typename T>
+__global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) == 8 ? 3 : 4)) spspmm_kernel(const SpParams p) {
+  constexpr bool NUMERIC = MODE != SP_SYM;
+  constexpr bool FUSED = MODE == SP_FUSED;
   extern __shared__ __align__(16) unsigned char smem[];
   const uint32_t WW = (uint32_t)p.window_bits >> 5;   // bitmap words (>= 32)
   const int lw = p.log2_wpt;
@@ -199,10 +246,9 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
   T* acc = reinterpret_cast<T*>(scol + kStageCap);                  // NUMERIC: kStageCap entries (flat path)
   uint32_t* tbase = reinterpret_cast<uint32_t*>(acc);               // NUMERIC: 256 entries (general path, aliases acc)
   __shared__ int s_warp[kSpWarps];
-  __shared__ unsigned int s_chunk;
-  __shared__ long long s_min, s_max;
-  __shared__ int64_t s_rp[kRowsPerGrab + 1];
-  __shared__ int64_t s_rpc[kRowsPerGrab];
+  __shared__ unsigned int s_claim[2];               // row tickets: the row being processed / the next one
+  __shared__ long long s_min, s_max, s_base;
+  __shared__ int s_total;
   __shared__ int64_t s_bs[kABatch];
   __shared__ int s_len[kABatch];
   __shared__ int2 s_se[kABatch];                    // flat path: [first, last+1) product number of each A entry
@@ -213,6 +259,7 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (uint32_t q = tid; q < WW; q += kSpThreads) bitmap[q] = 0;
   tflag[tid] = 0;
+  if (tid == 0) s_claim[0] = atomicAdd(p.counter, 1u);
 
   const T* va = reinterpret_cast<const T*>(p.val_a);
   const T* vb = reinterpret_cast<const T*>(p.val_b);
@@ -229,23 +276,50 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
   int pf_len = 0;
   T pf_av = (T)1;
 
-  while (true) {
-    __syncthreads();
-    if (tid == 0) s_chunk = atomicAdd(p.counter, (unsigned int)kRowsPerGrab);
-    __syncthreads();
-    const int64_t r0 = s_chunk;
-    if (r0 >= p.M) break;
-    const int nr = (int)min((int64_t)kRowsPerGrab, p.M - r0);
-    if (tid <= nr) s_rp[tid] = p.rowptr_a[r0 + tid];
-    if (NUMERIC && tid < nr) s_rpc[tid] = p.rowptr_c[r0 + tid];
-    __syncthreads();
-    pf_valid = false;
+  __syncthreads();
+  // Rows are handed out one at a time from a global ticket counter, one row AHEAD: the ticket of the next row is
+  // taken when a row starts, so its rowptr_a -> col_a -> rowptr_b chain of dependent loads overlaps this row's work.
+  int par = 0;
+  int64_t i = s_claim[0];
+  int64_t a_s = 0, a_e = 0;
+  if (i < p.M) { a_s = p.rowptr_a[i]; a_e = p.rowptr_a[i + 1]; }
 
-    for (int j = 0; j < nr; j++) {
-      const int64_t i = r0 + j;
-      const int64_t a_s = s_rp[j], a_e = s_rp[j + 1];
-      const int64_t n_a = a_e - a_s;
-      if (n_a <= 0) { pf_valid = false; continue; }  // counts[i] stays 0 (pre-zeroed); no output
+  while (i < p.M) {
+    if (tid == 0) s_claim[par ^ 1] = atomicAdd(p.counter, 1u);
+    const int64_t n_a = a_e - a_s;
+    int64_t nrow = p.M, nx_s = 0, nx_e = 0;   // the next row and its A-row extent
+    bool do_pf = false;
+    int64_t nk = -1;
+
+#define SP_NEXT_ROW()                                              \
+  nrow = s_claim[par ^ 1];                                         \
+  if (nrow < p.M) { nx_s = p.rowptr_a[nrow]; nx_e = p.rowptr_a[nrow + 1]; }
+#define SP_PF_STAGE1()                                             \
+  {                                                                \
+    const int64_t nn = nx_e - nx_s;                                \
+    if (nn > 0 && nn <= kABatch) {                                 \
+      do_pf = true;                                                \
+      if (tid < nn) nk = p.col_a[nx_s + tid];                      \
+    }                                                              \
+  }
+#define SP_PF_STAGE2()                                             \
+  if (do_pf) {                                                     \
+    if (nk >= 0) {                                                 \
+      pf_bs = p.rowptr_b[nk];                                      \
+      pf_len = (int)(p.rowptr_b[nk + 1] - pf_bs);                  \
+      pf_av = (NUMERIC && va) ? va[nx_s + tid] : (T)1;             \
+    }                                                              \
+    pf_valid = true;                                               \
+  }
+
+    do {  // one row; `break` = done with it
+      if (n_a <= 0) {  // empty row: counts[i] stays 0 (pre-zeroed) / status = aggregate 0; no output
+        if (FUSED && tid == 0) sp_st_status(p.status + i, kStAgg);
+        pf_valid = false;
+        __syncthreads();
+        SP_NEXT_ROW();
+        break;
+      }
       const int na0 = (int)min(n_a, (int64_t)kABatch);
 
       // ---- stage the (first batch of the) A-row metadata: start/length of each B row, a_ik; number the products ----
@@ -268,6 +342,7 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
       const int len_c = min(len, kStageCap + 1);  // keeps the sum in range; any clamped length disables the flat path
       int P;
       const int excl = sp_block_scan(len_c, s_warp, P);
+      SP_NEXT_ROW();   // the barrier inside the scan made the ticket visible; the two rowptr_a loads are in flight
       if (tid < na0) {
         s_se[tid] = make_int2(excl, excl + len_c);
         // the 32-aligned product numbers inside [excl, excl + len): this entry is where their chunk starts
@@ -275,27 +350,6 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
           for (int k = (excl + 31) >> 5; (k << 5) < excl + len_c; k++) s_ent[k] = (unsigned char)tid;
       }
       pf_valid = false;
-
-      // ---- issue the first load of the next row's metadata (completed mid-row) ----
-      bool do_pf = false;
-      int64_t nk = -1, nx_s = 0;
-      if (j + 1 < nr) {
-        nx_s = s_rp[j + 1];
-        const int64_t nn = s_rp[j + 2] - nx_s;
-        if (nn > 0 && nn <= kABatch) {
-          do_pf = true;
-          if (tid < nn) nk = p.col_a[nx_s + tid];
-        }
-      }
-#define SP_PF_STAGE2()                                             \
-  if (do_pf) {                                                     \
-    if (nk >= 0) {                                                 \
-      pf_bs = p.rowptr_b[nk];                                      \
-      pf_len = (int)(p.rowptr_b[nk + 1] - pf_bs);                  \
-      pf_av = (NUMERIC && va) ? va[nx_s + tid] : (T)1;             \
-    }                                                              \
-    pf_valid = true;                                               \
-  }
       __syncthreads();  // s_bs / s_len / s_se / s_ent / s_av visible
 
       const bool flat = !multi_window && n_a <= kABatch && P <= kStageCap;
@@ -320,6 +374,7 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
             }
           }
         }
+        SP_PF_STAGE1();
 #pragma unroll
         for (int u = 0; u < kFlatU; u++)
           if (cc[u] != 0xffffffffu) sp_mark(bitmap, cc[u]);
@@ -334,10 +389,12 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
 #pragma unroll
           for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
           if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + i), (unsigned long long)cnt);
-          continue;  // the next row's staging barriers order the clears before its marks
+          break;  // the next row's staging barriers order the clears before its marks
         }
         const int wc = sp_scan<true>(bitmap, pre4, tbase, tflag, lw, NCH, s_warp);
-        const int64_t ob = s_rpc[j];
+        // single pass: the row's nnz is known now -> publish it, so that later rows can add it up while this
+        // row is still ranking its products
+        if (FUSED && tid == 0) sp_st_status(p.status + i, kStAgg | (unsigned long long)wc);
         __syncthreads();
         // rank; every product writes (its id, its column) into the slot: the last writer owns the slot
 #pragma unroll
@@ -350,8 +407,8 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
           }
         }
         __syncthreads();
+        uint32_t dmask = 0;
         if (has_val) {
-          uint32_t dmask = 0;
 #pragma unroll
           for (int u = 0; u < kFlatU; u++) {
             if (cc[u] != 0xffffffffu) {
@@ -361,14 +418,31 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
               else dmask |= 1u << u;
             }
           }
-          if (__syncthreads_or(dmask != 0)) {
-#pragma unroll
-            for (int u = 0; u < kFlatU; u++)
-              if (dmask & (1u << u)) atomicAdd(&acc[cc[u] >> kMaxWindowLog2], pv[u]);
-            __syncthreads();
+        }
+        if (FUSED && warp == 0 && wc > 0) {
+          // where this row starts in the output: nnz of all earlier rows (decoupled look-back), then publish the
+          // inclusive prefix for the rows behind
+          const int64_t base = sp_lookback(p.status, i, lane);
+          if (lane == 0) {
+            sp_st_status(p.status + i, kStPrefix | (unsigned long long)(base + wc));
+            s_base = base;
           }
         }
-        for (int q = tid; q < wc; q += kSpThreads) {
+        if (__syncthreads_or(dmask != 0)) {
+#pragma unroll
+          for (int u = 0; u < kFlatU; u++)
+            if (dmask & (1u << u)) atomicAdd(&acc[cc[u] >> kMaxWindowLog2], pv[u]);
+          __syncthreads();
+        }
+        int64_t ob;
+        if (FUSED) ob = s_base;
+        else ob = p.rowptr_c[i];
+        int nw = wc;
+        if (FUSED && wc > 0 && ob + wc > p.capacity) {  // cannot happen with capacity >= sum of products; never write past it
+          nw = 0;
+          if (tid == 0) *p.overflow = 1;
+        }
+        for (int q = tid; q < nw; q += kSpThreads) {
           __stcs(p.col_c + ob + q, (int64_t)(scol[q] & (uint32_t)(kMaxWindowBits - 1)));
           if (p.row_c) __stcs(p.row_c + ob + q, i);
           if (has_val) __stcs(val_c + ob + q, acc[q]);
@@ -376,10 +450,11 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
 #pragma unroll
         for (int u = 0; u < kFlatU; u++)
           if (cc[u] != 0xffffffffu) bitmap[sp_phys((cc[u] & (uint32_t)(kMaxWindowBits - 1)) >> 5)] = 0;
-        continue;  // the next row's staging barriers order the clears / staging reads before its writes
+        break;  // the next row's staging barriers order the clears / staging reads before its writes
       }
 
       // ================= general row: products re-walked per pass, window by window =================
+      SP_PF_STAGE1();
       int64_t win_lo = 0, win_hi = 0;  // window index range [win_lo, win_hi]
       if (multi_window) {
         // B rows are column-sorted (SparseStorage invariant): first/last entry bound the row's columns
@@ -402,7 +477,8 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
       }
       const bool single_batch = n_a <= kABatch;
       int64_t done = 0;  // nnz of this row emitted by previous windows
-      const int64_t out0 = NUMERIC ? s_rpc[j] : 0;
+      int64_t out0 = 0;
+      if (MODE == SP_NUM) out0 = p.rowptr_c[i];
       int cnt = 0;       // symbolic: columns this thread was first on
 
       // walk every product of the row that falls into [wlo, whi); BODY sees c (column), c0 (window-relative),
@@ -433,25 +509,70 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
       }                                                                            \
     }                                                                              \
   }
+      // counting pass (the whole job of the symbolic kernel; in single-pass mode it gives the row's nnz before
+      // anything is written): mark with atomicOr, whose return value tells a product whether it was first
+#define SP_COUNT_PASS()                                                            \
+  for (int64_t win = win_lo; win <= win_hi; win++) {                               \
+    const int64_t wlo = win * W, whi = wlo + W;                                    \
+    SP_WALK({                                                                      \
+      const uint32_t bit = 1u << (c0 & 31u);                                       \
+      const uint32_t old = atomicOr(&bitmap[sp_phys(c0 >> 5)], bit);               \
+      if (!(old & bit)) cnt++;                                                     \
+      tflag[c0 >> (5 + lw)] = 1;                                                   \
+    })                                                                             \
+    __syncthreads();                                                               \
+    if ((uint32_t)tid < NCH && tflag[tid]) {                                       \
+      sp_count_clear_chunk(bitmap, lw);                                            \
+      tflag[tid] = 0;                                                              \
+    }                                                                              \
+    __syncthreads();                                                               \
+  }
 
-      for (int64_t win = win_lo; win <= win_hi; win++) {
-        const int64_t wlo = win * W, whi = wlo + W;
-        // ---- mark ----
-        SP_WALK({
-          const uint32_t bit = 1u << (c0 & 31u);
-          const uint32_t old = atomicOr(&bitmap[sp_phys(c0 >> 5)], bit);
-          if (!NUMERIC && !(old & bit)) cnt++;
-          tflag[c0 >> (5 + lw)] = 1;
-        })
+      if (!NUMERIC) {
+        SP_COUNT_PASS();
+#pragma unroll
+        for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + i), (unsigned long long)cnt);
+        SP_PF_STAGE2();
+        break;
+      }
+      bool skip_row = false;
+      if (FUSED) {
+        if (tid == 0) s_total = 0;
         __syncthreads();
-
-        if (!NUMERIC) {
-          // ---- clear touched chunks ----
-          if ((uint32_t)tid < NCH && tflag[tid]) {
-            sp_count_clear_chunk(bitmap, lw);
-            tflag[tid] = 0;
+        SP_COUNT_PASS();
+#pragma unroll
+        for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0 && cnt) atomicAdd(&s_total, cnt);
+        __syncthreads();
+        const int total = s_total;
+        if (warp == 0) {
+          if (lane == 0) sp_st_status(p.status + i, kStAgg | (unsigned long long)total);
+          if (total > 0) {
+            const int64_t base = sp_lookback(p.status, i, lane);
+            if (lane == 0) {
+              sp_st_status(p.status + i, kStPrefix | (unsigned long long)(base + total));
+              s_base = base;
+            }
           }
-        } else {
+        }
+        __syncthreads();
+        out0 = s_base;
+        if (total == 0) skip_row = true;
+        else if (out0 + total > p.capacity) {
+          skip_row = true;
+          if (tid == 0) *p.overflow = 1;
+        }
+      }
+      if (!skip_row) {
+        for (int64_t win = win_lo; win <= win_hi; win++) {
+          const int64_t wlo = win * W, whi = wlo + W;
+          // ---- mark ----
+          SP_WALK({
+            atomicOr(&bitmap[sp_phys(c0 >> 5)], 1u << (c0 & 31u));
+            tflag[c0 >> (5 + lw)] = 1;
+          })
+          __syncthreads();
           const int wc = sp_scan<false>(bitmap, pre4, tbase, tflag, lw, NCH, s_warp);
           const int64_t ob = out0 + done;
           const bool staged = wc <= kStageCap;  // columns staged in shared memory -> coalesced stores
@@ -482,22 +603,53 @@ __global__ void __launch_bounds__(kSpThreads, (NUMERIC && sizeof(T) == 8) ? 3 : 
             tflag[tid] = 0;
           }
           done += wc;
+          __syncthreads();
         }
-        __syncthreads();
       }
 #undef SP_WALK
-      if (!NUMERIC) {
-#pragma unroll
-        for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + i), (unsigned long long)cnt);
-      }
+#undef SP_COUNT_PASS
       SP_PF_STAGE2();
+    } while (false);
+#undef SP_PF_STAGE1
 #undef SP_PF_STAGE2
-    }
+#undef SP_NEXT_ROW
+    i = nrow;
+    a_s = nx_s;
+    a_e = nx_e;
+    par ^= 1;
   }
 }
 
+// FUSED mode epilogue: rowptr_c from the per-row status words. Rows with output carry their inclusive prefix; rows
+// without (aggregate 0) inherit the prefix of the nearest earlier row with output = a running maximum.
+__global__ void sp_status_value_kernel(const unsigned long long* __restrict__ status, int64_t M, int64_t* __restrict__ v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) {
+    const unsigned long long st = status[i];
+    v[i] = ((st >> 62) == 2) ? (int64_t)(st & kStMask) : 0;
+  }
+}
+
+// sum over the entries of A of the length of the B row they select = number of products = upper bound of nnz(C)
+__global__ void __launch_bounds__(256) sp_bound_kernel(const int64_t* __restrict__ col_a, int64_t nnz_a,
+                                                       const int64_t* __restrict__ rowptr_b,
+                                                       unsigned long long* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned long long s = 0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz_a; e += stride) {
+    const int64_t k = col_a[e];
+    s += (unsigned long long)(rowptr_b[k + 1] - rowptr_b[k]);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
 __global__ void sp_copy_last_kernel(const int64_t* rowptr_c, int64_t M, int64_t* nnz_dev) { *nnz_dev = rowptr_c[M]; }
+// nnz(C), or -1 when a row did not fit into the caller's arrays (nothing was written past them)
+__global__ void sp_finish_fused_kernel(const int64_t* rowptr_c, int64_t M, const int* overflow, int64_t* nnz_dev) {
+  *nnz_dev = *overflow ? (int64_t)-1 : rowptr_c[M];
+}
 
 static int window_bits_for(int64_t N) {
   int64_t w = 1024;
@@ -518,30 +670,34 @@ static size_t sp_smem_bytes(int window_bits, bool numeric, size_t elem) {
   return b;
 }
 
-struct SpLayout { size_t scalars, cub, total, cub_bytes; };
+struct SpLayout { size_t scalars, status, cub, total, cub_bytes; };
 static SpLayout sp_layout(int64_t M) {
   SpLayout L;
   size_t off = 0;
   L.scalars = off; off += 256;
-  size_t tb = 0;
+  L.status = off; off += align_up((size_t)(M > 0 ? M : 1) * 8, 256);
+  size_t tb = 0, tb2 = 0;
   cub::DeviceScan::InclusiveSum(nullptr, tb, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(M > 0 ? M : 1),
                                 (cudaStream_t)0);
-  L.cub_bytes = tb;
-  L.cub = off; off += align_up(tb, 256);
+  cub::DeviceScan::InclusiveScan(nullptr, tb2, (const int64_t*)nullptr, (int64_t*)nullptr, cub::Max(),
+                                 (int)(M > 0 ? M : 1), (cudaStream_t)0);
+  L.cub_bytes = tb > tb2 ? tb : tb2;
+  L.cub = off; off += align_up(L.cub_bytes, 256);
   L.total = off;
   return L;
 }
 
-template <bool NUMERIC, typename T> static int sp_launch(const SpParams& p, cudaStream_t st) {
-  const size_t smem = sp_smem_bytes(p.window_bits, NUMERIC, sizeof(T));
-  auto* k = spspmm_kernel<NUMERIC, T>;
+template <int MODE, typename T> static int sp_launch(const SpParams& p, cudaStream_t st) {
+  const size_t smem = sp_smem_bytes(p.window_bits, MODE != SP_SYM, sizeof(T));
+  auto* k = spspmm_kernel<MODE, T>;
   TSB_CUDA_TRY(cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   TSB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, kSpThreads, smem));
   if (per_sm < 1) per_sm = 1;
+  // persistent grid, never larger than what is resident at once: in single-pass mode a row waits for the rows
+  // before it, which must therefore belong to CTAs that are running
   int64_t grid = (int64_t)per_sm * num_sms();
-  const int64_t grabs = (p.M + kRowsPerGrab - 1) / kRowsPerGrab;
-  if (grid > grabs) grid = grabs;
+  if (grid > p.M) grid = p.M;
   if (grid < 1) grid = 1;
   k<<<(int)grid, kSpThreads, smem, st>>>(p);
   TSB_LAUNCH_CHECK();
@@ -583,7 +739,8 @@ extern "C" int tsb200_spspmm_symbolic(const int64_t* rowptr_a, const int64_t* co
   p.counter = (unsigned int*)(ws + L.scalars);
   p.window_bits = window_bits_for(N);
   p.log2_wpt = log2_wpt_for(p.window_bits);
-  int rc = sp_launch<false, float>(p, st);
+  p.status = nullptr; p.capacity = 0; p.overflow = nullptr;
+  int rc = sp_launch<SP_SYM, float>(p, st);
   if (rc) return rc;
   size_t tb = L.cub_bytes;
   TSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(ws + L.cub, tb, rowptr_c + 1, rowptr_c + 1, (int)M, st));
@@ -616,6 +773,76 @@ extern "C" int tsb200_spspmm_numeric(const int64_t* rowptr_a, const int64_t* col
   p.counter = (unsigned int*)(ws + L.scalars);
   p.window_bits = window_bits_for(N);
   p.log2_wpt = log2_wpt_for(p.window_bits);
-  if (val_c && dtype == TSB200_F64) return sp_launch<true, double>(p, st);
-  return sp_launch<true, float>(p, st);
+  p.status = nullptr; p.capacity = 0; p.overflow = nullptr;
+  if (val_c && dtype == TSB200_F64) return sp_launch<SP_NUM, double>(p, st);
+  return sp_launch<SP_NUM, float>(p, st);
+}
+
+extern "C" int tsb200_spspmm_bound(const int64_t* col_a, const int64_t* rowptr_b, int64_t nnz_a, void* workspace,
+                                   size_t workspace_bytes, int64_t* bound_host, void* stream) {
+  if (nnz_a < 0) return TSB200_ERR_INVALID_ARG;
+  if (!workspace || workspace_bytes < 256) return TSB200_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* d = (unsigned long long*)((char*)workspace + 32);
+  TSB_CUDA_TRY(cudaMemsetAsync(d, 0, 8, st));
+  if (nnz_a > 0) {
+    if (!col_a || !rowptr_b) return TSB200_ERR_INVALID_ARG;
+    int64_t blocks = (nnz_a + 1023) / 1024;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    sp_bound_kernel<<<(int)blocks, 256, 0, st>>>(col_a, nnz_a, rowptr_b, d);
+    TSB_LAUNCH_CHECK();
+  }
+  if (bound_host) TSB_CUDA_TRY(cudaMemcpyAsync(bound_host, d, 8, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" int tsb200_spspmm_fused(const int64_t* rowptr_a, const int64_t* col_a, const void* val_a,
+                                   const int64_t* rowptr_b, const int64_t* col_b, const void* val_b, int64_t M,
+                                   int64_t Kd, int64_t N, int64_t nnz_a, int64_t nnz_b, int64_t* rowptr_c,
+                                   int64_t* row_c, int64_t* col_c, void* val_c, int64_t capacity, int dtype,
+                                   void* workspace, size_t workspace_bytes, int64_t* nnz_c_host, void* stream) {
+  if (M < 0 || Kd < 0 || N < 0 || nnz_a < 0 || nnz_b < 0 || capacity < 0 || !rowptr_c) return TSB200_ERR_INVALID_ARG;
+  if (M >= ((int64_t)1 << 31)) return TSB200_ERR_UNSUPPORTED;
+  if (val_c && dtype != TSB200_F32 && dtype != TSB200_F64) return TSB200_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const SpLayout L = sp_layout(M);
+  if (!workspace || workspace_bytes < L.total) return TSB200_ERR_WORKSPACE;
+  char* ws = (char*)workspace;
+  // scalars: [0] row ticket, [16] nnz(C) (int64), [32] product bound (tsb200_spspmm_bound), [48] overflow flag
+  TSB_CUDA_TRY(cudaMemsetAsync(ws + L.scalars, 0, 32, st));
+  TSB_CUDA_TRY(cudaMemsetAsync(ws + L.scalars + 48, 0, 8, st));
+  TSB_CUDA_TRY(cudaMemsetAsync(rowptr_c, 0, (size_t)(M + 1) * 8, st));
+  int64_t* nnz_dev = (int64_t*)(ws + L.scalars + 16);
+  if (M == 0 || nnz_a == 0 || nnz_b == 0) {
+    if (nnz_c_host) { nnz_c_host[0] = 0; }
+    return 0;
+  }
+  if (!rowptr_a || !col_a || !rowptr_b || !col_b || (capacity > 0 && !col_c)) return TSB200_ERR_INVALID_ARG;
+  TSB_CUDA_TRY(cudaMemsetAsync(ws + L.status, 0, (size_t)M * 8, st));
+  SpParams p;
+  p.rowptr_a = rowptr_a; p.col_a = col_a; p.val_a = val_a;
+  p.rowptr_b = rowptr_b; p.col_b = col_b; p.val_b = val_b;
+  p.M = M; p.Kd = Kd; p.N = N;
+  p.counts = nullptr; p.rowptr_c = nullptr; p.row_c = row_c; p.col_c = col_c; p.val_c = val_c;
+  p.counter = (unsigned int*)(ws + L.scalars);
+  p.status = (unsigned long long*)(ws + L.status);
+  p.capacity = capacity;
+  p.overflow = (int*)(ws + L.scalars + 48);
+  p.window_bits = window_bits_for(N);
+  p.log2_wpt = log2_wpt_for(p.window_bits);
+  int rc = (val_c && dtype == TSB200_F64) ? sp_launch<SP_FUSED, double>(p, st) : sp_launch<SP_FUSED, float>(p, st);
+  if (rc) return rc;
+  // rowptr_c[1 + i] = running maximum of the published inclusive prefixes
+  int64_t blocks = (M + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  sp_status_value_kernel<<<(int)blocks, 256, 0, st>>>(p.status, M, rowptr_c + 1);
+  TSB_LAUNCH_CHECK();
+  size_t tb = L.cub_bytes;
+  TSB_CUDA_TRY(cub::DeviceScan::InclusiveScan(ws + L.cub, tb, rowptr_c + 1, rowptr_c + 1, cub::Max(), (int)M, st));
+  sp_finish_fused_kernel<<<1, 1, 0, st>>>(rowptr_c, M, p.overflow, nnz_dev);
+  TSB_LAUNCH_CHECK();
+  if (nnz_c_host) TSB_CUDA_TRY(cudaMemcpyAsync(nnz_c_host, nnz_dev, 8, cudaMemcpyDeviceToHost, st));
+  return 0;
 }

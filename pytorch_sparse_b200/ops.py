@@ -9,6 +9,7 @@ reference's CHECK_CUDA, csrc/cuda/utils.cuh:5-6) — there is no CPU path.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -135,6 +136,39 @@ def spmm_fw(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor,
         check(lib.tsb200_spmm_fw(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(arg_out),
                                  B, M, N, K, E, dt, red, _p(ws), nws, _stream(dev)), "tsb200_spmm_fw")
     return out, arg_out
+
+
+def spmm_fw_acc(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor, partial: Tensor,
+                out: Optional[Tensor], acc_mode: int) -> None:
+    """One column block of a SUM SpMM whose blocks are launched separately (tsb200_spmm_fw_acc): `partial` is the
+    fp32 [.., M, K] accumulator shared by the blocks; acc_mode 1 = first block, 2 = middle, 3 = last (writes `out`)."""
+    for t, n in ((rowptr, "rowptr"), (col, "col"), (mat, "mat"), (partial, "partial")):
+        _check_cuda(t, n)
+    _check_input(acc_mode in (1, 2, 3) and partial.dtype == torch.float32 and partial.is_contiguous())
+    _check_input(mat.is_contiguous() and (value is None or (value.dtype == mat.dtype and value.is_contiguous())))
+    rowptr, col = _i64(rowptr, "rowptr"), _i64(col, "col")
+    M = rowptr.numel() - 1
+    N, K = mat.size(-2), mat.size(-1)
+    B = mat.numel() // (N * K) if N * K > 0 else 0
+    E = col.numel()
+    _check_input(partial.numel() == B * M * K)
+    if acc_mode == 3:
+        _check_input(out is not None and out.dtype == mat.dtype and out.is_contiguous() and out.numel() == B * M * K)
+    if B * M * K == 0:
+        return
+    if E == 0:  # an empty column block contributes nothing
+        if acc_mode == 1:
+            partial.zero_()
+        elif acc_mode == 3:
+            out.copy_(partial.view(out.shape))
+        return
+    dev = mat.device
+    dt = _dtype_code(mat.dtype)
+    with _on_device(dev):
+        nws = lib.tsb200_spmm_fw_workspace_bytes(B, M, K, E, dt, 0)
+        ws = _workspace(nws, dev)
+        check(lib.tsb200_spmm_fw_acc(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(partial), acc_mode,
+                                     B, M, N, K, E, dt, _p(ws), nws, _stream(dev)), "tsb200_spmm_fw_acc")
 
 
 def spmm_value_bw(row: Tensor, rowptr: Tensor, col: Tensor, mat: Tensor, grad: Tensor,
@@ -323,7 +357,7 @@ class _PinnedScalar:
     _pool: list = []
 
     def __init__(self):
-        self.t = self._pool.pop() if self._pool else torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.t = self._pool.pop() if self._pool else torch.zeros(1, dtype=torch.int64, device="cpu").pin_memory()
 
     def ptr(self):
         return ctypes.c_void_p(self.t.data_ptr())
@@ -456,11 +490,40 @@ def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: T
         val_a = val_b = None
     nnz_a, nnz_b = col_a.numel(), col_b.numel()
     rowptr_c = torch.empty(M + 1, dtype=torch.int64, device=dev)
+    esize = 0 if not want_value else (8 if dtype == torch.float64 else 4)
+    mode = os.environ.get("TSB200_SPSPMM", "auto")   # auto | fused | two_phase
     with _on_device(dev):
         nws = lib.tsb200_spspmm_workspace_bytes(M, Kd, N, nnz_a, nnz_b)
         ws = _workspace(nws, dev)
         st = _stream(dev)
         pin = _PinnedScalar()
+        if mode != "two_phase":
+            # single pass: output arrays sized by the number of products (an upper bound of nnz(C)); taken when that
+            # bound fits comfortably into the memory still available, otherwise count first (two phases)
+            check(lib.tsb200_spspmm_bound(_p(col_a), _p(rowptr_b), nnz_a, _p(ws), nws, pin.ptr(), st),
+                  "tsb200_spspmm_bound")
+            torch.cuda.current_stream(dev).synchronize()
+            bound = pin.read()
+            pin = _PinnedScalar()
+            if mode == "fused" or bound * (16 + esize) <= 0.45 * _available_bytes(dev):
+                row_c = torch.empty(bound, dtype=torch.int64, device=dev)
+                col_c = torch.empty(bound, dtype=torch.int64, device=dev)
+                val_c = torch.empty(bound, dtype=dtype, device=dev) if want_value else None
+                check(lib.tsb200_spspmm_fused(_p(rowptr_a), _p(col_a), _p(val_a), _p(rowptr_b), _p(col_b), _p(val_b),
+                                              M, Kd, N, nnz_a, nnz_b, _p(rowptr_c), _p(row_c), _p(col_c), _p(val_c),
+                                              bound, _dtype_code(dtype) if want_value else 0, _p(ws), nws, pin.ptr(),
+                                              st), "tsb200_spspmm_fused")
+                torch.cuda.current_stream(dev).synchronize()
+                nnz_c = pin.read()
+                if nnz_c < 0:  # cannot happen with capacity = number of products
+                    raise _lib.Tsb200Error("tsb200_spspmm_fused: output capacity exceeded")
+                row_c, col_c = row_c[:nnz_c], col_c[:nnz_c]
+                val_c = None if val_c is None else val_c[:nnz_c]
+                if nnz_c < 0.75 * bound:  # many merged products: do not keep the oversized allocations alive
+                    row_c, col_c = row_c.clone(), col_c.clone()
+                    val_c = None if val_c is None else val_c.clone()
+                return rowptr_c, row_c, col_c, val_c
+            pin = _PinnedScalar()
         check(lib.tsb200_spspmm_symbolic(_p(rowptr_a), _p(col_a), _p(rowptr_b), _p(col_b), M, Kd, N, nnz_a,
                                          nnz_b, _p(rowptr_c), _p(ws), nws, pin.ptr(), st),
               "tsb200_spspmm_symbolic")
@@ -477,6 +540,12 @@ def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: T
     return rowptr_c, row_c, col_c, val_c
 
 
+def _available_bytes(dev: torch.device) -> int:
+    """Device memory a new allocation can draw on: free on the device plus what PyTorch's allocator holds unused."""
+    free, _total = torch.cuda.mem_get_info(dev)
+    return int(free) + int(torch.cuda.memory_reserved(dev)) - int(torch.cuda.memory_allocated(dev))
+
+
 _PINNED_POOL: dict = {}   # nbytes -> list of (pinned uint8 tensor, idle use-count); cudaHostAlloc of 256 MB costs ~30 ms
 
 
@@ -488,7 +557,7 @@ def _pinned_empty(shape, dtype: torch.dtype, pin: bool = True) -> Tensor:
     """A pinned host tensor from a small pool. A pooled buffer is handed out again only when no tensor other
     than the pool's own handle references its storage any more (every view a caller derived from an earlier
     result holds a storage reference, so the C++ use-count tells)."""
-    esize = torch.empty(0, dtype=dtype).element_size()
+    esize = torch.empty(0, dtype=dtype, device="cpu").element_size()
     numel = int(torch.Size(shape).numel())
     nbytes = max(1, numel * esize)
     bucket = _PINNED_POOL.setdefault((nbytes, pin), [])
@@ -498,7 +567,7 @@ def _pinned_empty(shape, dtype: torch.dtype, pin: bool = True) -> Tensor:
             base = cand
             break
     if base is None:
-        base = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pin)
+        base = torch.empty(nbytes, dtype=torch.uint8, device="cpu", pin_memory=pin)
         if len(bucket) < 4:
             bucket.append((base, _storage_uses(base)))
     return base[:numel * esize].view(dtype).view(shape)
@@ -521,7 +590,7 @@ def spmm_fw_host(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tens
     B = mat.numel() // (N * K) if N * K > 0 else 0
     sizes = list(mat.shape)
     sizes[-2] = M
-    alloc = _pinned_empty if mat.is_pinned() else (lambda shape, dtype: torch.empty(shape, dtype=dtype))
+    alloc = _pinned_empty if mat.is_pinned() else (lambda shape, dtype: torch.empty(shape, dtype=dtype, device="cpu"))
     if out is None:
         out = alloc(sizes, mat.dtype)
     else:

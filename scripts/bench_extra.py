@@ -155,20 +155,31 @@ if "c3" in which:  # SpMM_max fwd + bwd, power-law, F=256 fp32 (BASELINE configs
         fwd_alg_gbs=bench.algorithmic_bytes(M, N, E, F, 4, True) / t_f / 1e6)
 
 if "c4" in which:  # SpSpMM 256k x 256k, 32 nnz/row, fp32 (BASELINE configs[3])
+    import os
     M = 262_144
     ra, rpa, ca = fast_random_csr(M, M, 32, 3, dev)
     rb, rpb, cb = fast_random_csr(M, M, 32, 4, dev)
     va = torch.randn(ca.numel(), device=dev); vb = torch.randn(cb.numel(), device=dev)
+    from pytorch_sparse_b200._lib import lib
+    from pytorch_sparse_b200.ops import _p, _stream, _workspace
     res = {}
     def run():
         res["c"] = ops.spspmm(rpa, ca, va, rpb, cb, vb, M, M, M, True)
-    torch.cuda.synchronize(); t0 = time.perf_counter(); run(); torch.cuda.synchronize(); t_first = (time.perf_counter() - t0) * 1e3
-    t = timeit(run, 5, 2)   # two warm-ups: the caching allocator needs both output sets (old result alive while the new one is built)
-    nnz = res["c"][2].numel()
-    # the two kernels alone (no allocation, no nnz readback): C-ABI calls on preallocated outputs
-    from pytorch_sparse_b200._lib import lib
-    from pytorch_sparse_b200.ops import _p, _stream, _workspace
-    rp_c, r_c, c_c, v_c = res["c"]
+    ref = None
+    for mode in ("two_phase", "fused"):
+        os.environ["TSB200_SPSPMM"] = mode
+        torch.cuda.synchronize(); t0 = time.perf_counter(); run(); torch.cuda.synchronize(); t_first = (time.perf_counter() - t0) * 1e3
+        t = timeit(run, 5, 2)   # two warm-ups: the caching allocator needs both output sets (old result alive while the new one is built)
+        rp_c, r_c, c_c, v_c = res["c"]
+        nnz = c_c.numel()
+        if ref is None:
+            ref = (rp_c.clone(), c_c.clone(), v_c.clone())
+        else:  # both paths agree: structure bit-exact, values to rounding (accumulation order of duplicates)
+            assert torch.equal(rp_c, ref[0]) and torch.equal(c_c, ref[1])
+            assert torch.allclose(v_c, ref[2], rtol=1e-4, atol=1e-5)
+        out(what="c4_spspmm_f32", mode=mode, ms=t, first_ms=t_first, nnz_a=ca.numel(), nnz_b=cb.numel(), nnz_c=nnz,
+            out_gbs=nnz * 20 / t / 1e6, Gnnz_per_s=nnz / t / 1e6)
+    # the kernels alone (no allocation, no nnz readback): C-ABI calls on preallocated outputs
     nws = lib.tsb200_spspmm_workspace_bytes(M, M, M, ca.numel(), cb.numel()); ws = _workspace(nws, torch.device(dev)); st = _stream(torch.device(dev))
     rp_tmp = torch.empty_like(rp_c)
     t_sym = timeit(lambda: lib.tsb200_spspmm_symbolic(_p(rpa), _p(ca), _p(rpb), _p(cb), M, M, M, ca.numel(), cb.numel(),
@@ -176,11 +187,15 @@ if "c4" in which:  # SpSpMM 256k x 256k, 32 nnz/row, fp32 (BASELINE configs[3])
     assert torch.equal(rp_tmp, rp_c)
     t_num = timeit(lambda: lib.tsb200_spspmm_numeric(_p(rpa), _p(ca), _p(va), _p(rpb), _p(cb), _p(vb), M, M, M, ca.numel(),
                                                     cb.numel(), _p(rp_c), _p(r_c), _p(c_c), _p(v_c), 0, _p(ws), nws, st), 5, 1)
-    out(what="c4_spspmm_kernels", symbolic_ms=t_sym, numeric_ms=t_num, numeric_out_gbs=nnz * 20 / t_num / 1e6,
-        products=int(((rpb[1:] - rpb[:-1])[ca]).sum()))
-    del res, rp_c, r_c, c_c, v_c
-    out(what="c4_spspmm_f32", ms=t, first_ms=t_first, nnz_a=ca.numel(), nnz_b=cb.numel(), nnz_c=nnz, out_gbs=nnz * 20 / t / 1e6,
-        Gnnz_per_s=nnz / t / 1e6)
+    products = int(((rpb[1:] - rpb[:-1])[ca]).sum())
+    r2 = torch.empty(products, dtype=torch.long, device=dev); c2 = torch.empty_like(r2); v2 = torch.empty(products, device=dev)
+    t_fused = timeit(lambda: lib.tsb200_spspmm_fused(_p(rpa), _p(ca), _p(va), _p(rpb), _p(cb), _p(vb), M, M, M, ca.numel(),
+                                                    cb.numel(), _p(rp_tmp), _p(r2), _p(c2), _p(v2), products, 0, _p(ws), nws,
+                                                    None, st), 5, 1)
+    assert torch.equal(rp_tmp, rp_c) and torch.equal(c2[:nnz], c_c) and torch.equal(r2[:nnz], r_c)
+    out(what="c4_spspmm_kernels", symbolic_ms=t_sym, numeric_ms=t_num, fused_ms=t_fused, numeric_out_gbs=nnz * 20 / t_num / 1e6,
+        fused_out_gbs=nnz * 20 / t_fused / 1e6, products=products)
+    del res, rp_c, r_c, c_c, v_c, r2, c2, v2, ref
 
 if "coalesce" in which:
     M = N = 262_144

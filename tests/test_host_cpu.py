@@ -155,36 +155,55 @@ sys.path.insert(0, "%(root)s"); sys.path.insert(0, "%(root)s/tests")
 import oracle
 import pytorch_sparse_b200 as ts
 from pytorch_sparse_b200 import ops
-from pytorch_sparse_b200.parallel import RowShardedSpMM
+from pytorch_sparse_b200.parallel import RowShardedSpMM, PipelinedRowShardedSpMM
 ops.spmm_fw = lambda rowptr, col, value, mat, reduce: oracle.spmm(rowptr, col, value, mat, reduce)
 ops.spmm_value_bw = oracle.spmm_value_bw
+def _acc(rowptr, col, value, mat, partial, out, mode):      # CPU stand-in of tsb200_spmm_fw_acc (oracle kernels)
+    res = oracle.spmm(rowptr, col, value, mat, "sum")[0].float()
+    if mode == 1: partial.copy_(res)
+    elif mode == 2: partial.add_(res)
+    else: out.copy_((partial + res).to(out.dtype))
+ops.spmm_fw_acc = _acc
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 g = torch.Generator().manual_seed(0)
-M = N = 64; K = 8
-dense = (torch.rand(M, N, generator=g) < 0.1).double() * torch.randn(M, N, generator=g, dtype=torch.float64)
-x = torch.randn(N, K, generator=g, dtype=torch.float64)
-full = ts.SparseTensor.from_dense(dense)
-a_local = RowShardedSpMM.partition(full, rank, world)
-per = M // world
-x_local = x[rank * per:(rank + 1) * per].clone().requires_grad_()
-op = RowShardedSpMM(a_local.requires_grad_(), "sum")
-y_local = op(x_local)
-ref = dense @ x
-assert torch.allclose(y_local, ref[rank * per:(rank + 1) * per], atol=1e-12), "forward shard mismatch"
-go = torch.randn(M, K, generator=g, dtype=torch.float64)
-y_local.backward(go[rank * per:(rank + 1) * per])
-gx = dense.t() @ go                      # needs the reduce-scatter of the per-rank partials
-assert torch.allclose(x_local.grad, gx[rank * per:(rank + 1) * per], atol=1e-12), "grad_X shard mismatch"
-assert a_local.storage.value().grad is not None
+K = 8
+for M, N in ((64, 64), (65, 67)):        # 65 / 67: the last row blocks are shorter -> padded gather
+    dense = (torch.rand(M, N, generator=g) < 0.1).double() * torch.randn(M, N, generator=g, dtype=torch.float64)
+    x = torch.randn(N, K, generator=g, dtype=torch.float64)
+    full = ts.SparseTensor.from_dense(dense)
+    a_local = RowShardedSpMM.partition(full, rank, world)
+    pm, pn = RowShardedSpMM.block_rows(M, world), RowShardedSpMM.block_rows(N, world)
+    x_local = x[rank * pn:(rank + 1) * pn].clone().requires_grad_()
+    op = RowShardedSpMM(a_local.requires_grad_(), "sum")
+    y_local = op(x_local)
+    ref = dense @ x
+    assert torch.allclose(y_local, ref[rank * pm:(rank + 1) * pm], atol=1e-12), "forward shard mismatch"
+    go = torch.randn(M, K, generator=g, dtype=torch.float64)
+    y_local.backward(go[rank * pm:(rank + 1) * pm])
+    gx = dense.t() @ go                      # needs the reduce-scatter of the per-rank partials
+    assert x_local.grad.shape == x_local.shape
+    assert torch.allclose(x_local.grad, gx[rank * pn:(rank + 1) * pn], atol=1e-12), "grad_X shard mismatch"
+    assert a_local.storage.value().grad is not None
+# pipelined gather + column-chunk SpMM (the gather is part of the step)
+M, block, C = 48, 24, 4
+N = world * block
+dense = ((torch.rand(world * M, N, generator=g) < 0.15).float() * torch.randn(world * M, N, generator=g))
+x = torch.randn(N, K, generator=g)
+a_local = ts.SparseTensor.from_dense(dense[rank * M:(rank + 1) * M])
+pipe = PipelinedRowShardedSpMM(a_local, block=block, chunks=C)
+for _ in range(2):                           # buffers are reused across steps
+    y = pipe(x[rank * block:(rank + 1) * block].contiguous())
+    assert torch.allclose(y, (dense @ x)[rank * M:(rank + 1) * M], atol=1e-4), "pipelined shard mismatch"
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
 
 
 def test_row_sharded_spmm_gloo_world2(oracle, tmp_path):
-    """N>1 path on CPU: 2 ranks over gloo, row-block partition, all-gather of X, local SpMM (oracle
-    kernels), reduce-scatter of grad_X — forward and backward match the dense product."""
+    """N>1 path on CPU: 2 ranks over gloo, row-block partition (equal and ragged block heights), all-gather of
+    X, local SpMM (oracle kernels), reduce-scatter of grad_X — forward and backward match the dense product; and
+    the pipelined variant (chunked gather + column-chunk SpMM with an fp32 partial)."""
     script = tmp_path / "gloo_worker.py"
     script.write_text(_GLOO % {"root": str(ROOT)})
     env = dict(os.environ, TSB200_REGISTER_TORCH_SPARSE="0")

@@ -11,6 +11,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["fused", "two_phase"])
+def spspmm_mode(request, monkeypatch):
+    """Every test runs through both native paths: the single-pass kernel (row placement by decoupled look-back)
+    and the symbolic + numeric pair."""
+    monkeypatch.setenv("TSB200_SPSPMM", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("dtype", [torch.float, torch.double])
 def test_functional_known_answer(dtype):
     """test/test_spspmm.py:10-22"""
