@@ -395,7 +395,7 @@ spmm_vec_kernel(const SpmmParams p) {
   ring.col = p.col;
   ring.val = (const T*)p.value;
   ring.limit = p.E;
-  const uint64_t pol = make_policy_evict_last();
+  const uint64_t pol = mat_policy(p);
 
   bool col_ok[CH];
 #pragma unroll
@@ -515,7 +515,7 @@ spmm_gpr_kernel(const SpmmParams p) {
   const bool col_ok = p.k0 + li * VEC < p.K;
   const uint32_t row_bytes = (uint32_t)(p.K * (int64_t)sizeof(T));
   const int64_t lane_off = ((int64_t)p.k0 + (int64_t)li * VEC) * (int64_t)sizeof(T);
-  const uint64_t pol = make_policy_evict_last();
+  const uint64_t pol = mat_policy(p);
   const T* __restrict__ val = (const T*)p.value;
   const bool has_val = val != nullptr;
 
@@ -669,7 +669,7 @@ spmm_seg_kernel(const SpmmParams p) {
   ring.col = p.col;
   ring.val = (const T*)p.value;
   ring.limit = p.E;
-  const uint64_t pol = make_policy_evict_last();
+  const uint64_t pol = mat_policy(p);
 
   bool col_ok[CH];
 #pragma unroll
@@ -929,6 +929,7 @@ extern "C" int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
     p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = arg_out;
     p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
     p.partial = nullptr; p.acc_mode = 0;
+    choose_pin(p, (size_t)B * N * K * dtype_size(dtype));
     p.counters = (unsigned int*)(ws + L.counters);
     p.segs = (Segment*)(ws + L.segs);
     p.longs = (LongRow*)(ws + L.longs);
@@ -977,6 +978,7 @@ extern "C" int tsb200_spmm_fw_acc(const int64_t* rowptr, const int64_t* col, con
   p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = nullptr;
   p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
   p.partial = partial; p.acc_mode = acc_mode;
+  choose_pin(p, (size_t)B * N * K * dtype_size(dtype));
   p.counters = (unsigned int*)(ws + L.counters);
   p.segs = (Segment*)(ws + L.segs);
   p.longs = (LongRow*)(ws + L.longs);

@@ -227,12 +227,13 @@ def test_full_size_properties():
     assert torch.equal(prod, ym[pick])
 
 
-def test_full_size_c2_vs_oracle(oracle):
-    """BASELINE configs[1] at FULL size, directly against the oracle (fp32 restatement on the bf16
-    inputs, OpenMP over rows): every one of the 128M outputs within 1e-2 of the |A||B| bound, and the
-    fp32 kernel within 1e-5."""
+@pytest.mark.parametrize("wl", ["c2", "c2_f32", "c2_f256"])
+def test_full_size_c2_vs_oracle(oracle, wl):
+    """BASELINE configs[1] at FULL size and its F = 32 / F = 256 variants (north_star: F in {32, 128, 256}),
+    directly against the oracle (fp32 restatement on the bf16 inputs, OpenMP over rows): every output within 1e-2
+    of the |A||B| bound, and the fp32 kernel within 1e-5."""
     import bench
-    w = bench.WORKLOADS["c2"]
+    w = bench.WORKLOADS[wl]
     rowptr, col, value, N = bench.gen_matrix(w, 0, 1)
     x = bench.gen_dense(w, 0, N)
     vb, xb = value.bfloat16(), x.bfloat16()
@@ -264,5 +265,10 @@ def test_full_size_c3_max_vs_oracle(oracle):
     go = torch.randn(w["M"], w["F"], generator=g)
     gv, gm = ops.spmm_minmax_bw(col.to(DEV), value.to(DEV), x.to(DEV), go.to(DEV), arg, True, True)
     rv, rm = oracle.spmm_minmax_bw(col, value.double(), x.double(), go.double(), rarg)
-    assert torch.allclose(gv.cpu().double(), rv, rtol=1e-4, atol=1e-4)
-    assert torch.allclose(gm.cpu().double(), rm, rtol=1e-4, atol=1e-4)
+    # north_star tolerance: 1e-5 relative in fp32, against the componentwise |A||B| normaliser — the
+    # same routing applied to the absolute values bounds every accumulated sum. The kernel adds in fp32 with atomics
+    # (run-dependent order): the error of a sum of n terms is <= n * 2^-24 * sum|terms|, n <= K = 256 for
+    # grad_value and <= the column degree for grad_mat, i.e. <= 1.6e-5 worst case and ~sqrt(n) * 6e-8 in practice.
+    bv, bm = oracle.spmm_minmax_bw(col, value.double().abs(), x.double().abs(), go.double().abs(), rarg)
+    assert ((gv.cpu().double() - rv).abs() <= 1e-5 * bv + 1e-30).all()
+    assert ((gm.cpu().double() - rm).abs() <= 1e-5 * bm + 1e-30).all()
