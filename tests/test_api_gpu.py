@@ -125,3 +125,29 @@ def test_torchscript_function_over_registered_ops():
     assert torch.equal(row, a.storage.row())
     assert torch.allclose(out, dense.to("cuda:0") @ x, atol=1e-5)
     assert torch.equal(mx, ts.matmul(a, x, "max"))
+
+
+def test_torchscript_functional_pipeline_over_every_native_op():
+    """coalesce -> ind2ptr -> spspmm -> segment_reduce from ONE TorchScript function (torch.ops.tsb200.*): the
+    reference's scripted Python layer is built the same way on its registered ops."""
+    @torch.jit.script
+    def scripted(index: torch.Tensor, value: torch.Tensor, m: int):
+        row, col, val = torch.ops.tsb200.coalesce(index[0], index[1], value, m, m, "add")
+        assert val is not None
+        rowptr = torch.ops.tsb200.ind2ptr(row, m)
+        perm, colptr, row_csc = torch.ops.tsb200.csr2csc(row, col, m, m)
+        rp, r, c, v = torch.ops.tsb200.spspmm(rowptr, col, val, rowptr, col, val, m, m, m, True)
+        deg = torch.ops.tsb200.segment_reduce(rowptr, val, "sum", None, None)
+        return row, col, val, rp, r, c, v, deg, colptr
+
+    g = torch.Generator().manual_seed(11)
+    m, E = 50, 400
+    index = torch.randint(m, (2, E), generator=g).to("cuda:0")
+    value = torch.randn(E, generator=g, dtype=torch.float64).to("cuda:0")
+    row, col, val, rp, r, c, v, deg, colptr = scripted(index, value, m)
+    dense = torch.zeros(m, m, dtype=torch.float64, device="cuda:0").index_put((index[0], index[1]), value, accumulate=True)
+    a = ts.SparseTensor(row=row, col=col, value=val, sparse_sizes=(m, m), is_sorted=True)
+    assert torch.allclose(a.to_dense(), dense)
+    prod = ts.SparseTensor(row=r, col=c, value=v, sparse_sizes=(m, m), is_sorted=True).to_dense()
+    assert torch.allclose(prod, dense @ dense, atol=1e-10)
+    assert torch.allclose(deg, dense.sum(1)) and torch.equal(colptr, a.storage.colptr())
