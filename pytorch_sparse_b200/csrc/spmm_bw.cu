@@ -14,10 +14,6 @@
 
 #include "spmm_common.cuh"
 
-#ifndef TSB200_SDDMM_PREDICATED
-#define TSB200_SDDMM_PREDICATED 0
-#endif
-
 namespace tsb {
 
 template <typename T, int VEC> struct Vec16;
@@ -191,12 +187,11 @@ template <typename T, int LPR, int CH, int U> struct SddmmEngine {
       const int jrel = jend - j0 - g;
       uint4 d[U][CH];
       float part[U];
-#if TSB200_SDDMM_PREDICATED
-      // Branch-free variant (NOT enabled: written after the round's GPU budget was spent, never run — see
-      // profiles/r01_ncu_late_captures.md, the kernel is issue-bound and ~35 of its ~250 instructions per chunk are
-      // branches around the inline-asm gathers): gathers predicated inside the asm into zeroed registers, the dot
-      // products run unconditionally (an inactive slot contributes 0). The ring slot is read unconditionally — slots
-      // past the row's end hold stale but in-bounds column words, and the predicate keeps them from being dereferenced.
+      // Branch-free chunk (the kernel is issue-bound, profiles/r01_ncu_late_captures.md: ~35 of its ~250 instructions
+      // per chunk were branches around the inline-asm gathers): the gathers are predicated inside the asm into zeroed
+      // registers and the dot products run unconditionally (an inactive slot contributes 0). The ring slot is read
+      // unconditionally — slots past the row's end hold stale but in-bounds column words, and the predicate keeps
+      // them from being dereferenced. Measured on B200 at C2: 0.735 -> 0.571 ms (profiles/r02_results.md).
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const bool act = (u < nst) && (u * G < jrel);
@@ -215,30 +210,6 @@ template <typename T, int LPR, int CH, int U> struct SddmmEngine {
         for (int ch = 0; ch < CH; ch++) sdot += Vec16<T, VEC>::dot(d[u][ch], gq[ch]);
         part[u] = sdot;
       }
-#else
-      bool act[U];
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        act[u] = (u < nst) && (u * G < jrel);
-        if (act[u]) {
-          const uint32_t c = pc[2 * u * G];
-          const char* src = matb + (uint64_t)c * row_bytes;
-#pragma unroll
-          for (int ch = 0; ch < CH; ch++)
-            if (col_ok[ch]) d[u][ch] = ldg128_hint(src + ch * (LPR * 16), pol);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; u++) {
-        float sdot = 0.f;
-        if (act[u]) {
-#pragma unroll
-          for (int ch = 0; ch < CH; ch++)
-            if (col_ok[ch]) sdot += Vec16<T, VEC>::dot(d[u][ch], gq[ch]);
-        }
-        part[u] = sdot;
-      }
-#endif
       // lane li of group g gets the total of step li / (LPR/U); nnz t = u*G + g of the chunk goes to lane t
       const float tot = multi_reduce<U, LPR / 2>(part, li);
       const bool mine = lane < jend - j0;

@@ -44,6 +44,7 @@ constexpr int kFlatU = 8;                         // products per thread on the 
 constexpr int kStageCap = kFlatU * kSpThreads;    // output entries staged in shared memory per row (2048)
 constexpr int kMaxWindowLog2 = 18;
 constexpr int kMaxWindowBits = 1 << kMaxWindowLog2;
+constexpr int kClaimSlotDefault = 0;              // single-pass mode: schedule slot of the next row's ticket (see the kernel)
 constexpr int kABatch = 128;                      // A entries staged per batch
 static_assert(kStageCap <= (1 << (32 - kMaxWindowLog2 - 1)), "owner id and column share one 32-bit word");
 
@@ -58,6 +59,8 @@ struct SpParams {
   unsigned long long* status;  // FUSED: per-row look-back words (zeroed by the host)
   int64_t capacity;            // FUSED: entries the output arrays can hold
   int* overflow;               // FUSED: set when a row would not fit
+  unsigned long long* dbg;     // FUSED: optional look-back statistics (steps, empty polls, look-backs)
+  int claim_slot;              // where in a row's schedule the NEXT row's ticket is taken (0 = at the start)
   int window_bits;  // power of two, 1024 .. 2^18
   int log2_wpt;     // log2(bitmap words per scan chunk), 2..5; chunks = (window_bits/32) >> log2_wpt <= 256
 };
@@ -209,14 +212,18 @@ __device__ __forceinline__ void sp_st_status(unsigned long long* q, unsigned lon
 // One warp: number of output entries of all rows < i. Lane l inspects row j - l; a row that has published its
 // inclusive prefix ends the walk. Rows are claimed in increasing order by CTAs that are running, and a row's
 // aggregate depends on no other row, so every predecessor's status eventually becomes non-zero.
-__device__ __forceinline__ int64_t sp_lookback(const unsigned long long* status, int64_t i, int lane) {
+__device__ __forceinline__ int64_t sp_lookback(const unsigned long long* status, int64_t i, int lane,
+                                               unsigned long long* dbg) {
   int64_t excl = 0;
+  unsigned steps = 0, polls = 0;
   for (int64_t j = i - 1; j >= 0; j -= 32) {
     const int64_t r = j - lane;
     unsigned long long st = kStPrefix;  // rows before row 0: inclusive prefix 0
+    steps++;
     if (r >= 0) {
       st = sp_ld_status(status + r);
       while ((st >> 62) == 0) {
+        polls++;
         __nanosleep(40);
         st = sp_ld_status(status + r);
       }
@@ -228,6 +235,15 @@ __device__ __forceinline__ int64_t sp_lookback(const unsigned long long* status,
     for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     excl += v;
     if (pm) break;
+  }
+  if (dbg) {  // tuning aid (TSB200_SPSPMM_DEBUG): look-back steps and status polls that found nothing yet
+#pragma unroll
+    for (int off = 16; off; off >>= 1) polls += __shfl_xor_sync(0xffffffffu, polls, off);
+    if (lane == 0) {
+      atomicAdd(dbg, (unsigned long long)steps);
+      atomicAdd(dbg + 1, (unsigned long long)polls);
+      atomicAdd(dbg + 2, 1ull);
+    }
   }
   return excl;
 }
@@ -284,12 +300,17 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
   int64_t a_s = 0, a_e = 0;
   if (i < p.M) { a_s = p.rowptr_a[i]; a_e = p.rowptr_a[i + 1]; }
 
+  // The next row's ticket is taken at schedule slot `cs` of the current row, read after the following barrier
+  // (slot cs + 1), and its metadata chain is issued at slots cs + 2 / cs + 3. Slot 0 = row start (longest prefetch
+  // distance); later slots shorten the time between taking a ticket and publishing that row's nnz, which is what
+  // the rows behind it wait for in single-pass mode.
+  const int cs = FUSED ? p.claim_slot : 0;
   while (i < p.M) {
-    if (tid == 0) s_claim[par ^ 1] = atomicAdd(p.counter, 1u);
     const int64_t n_a = a_e - a_s;
     int64_t nrow = p.M, nx_s = 0, nx_e = 0;   // the next row and its A-row extent
     bool do_pf = false;
     int64_t nk = -1;
+    int stage = 0;  // 0 nothing yet, 1 ticket taken, 2 next row known, 3 its col_a issued, 4 its rowptr_b issued
 
 #define SP_NEXT_ROW()                                              \
   nrow = s_claim[par ^ 1];                                         \
@@ -312,14 +333,23 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
     pf_valid = true;                                               \
   }
 
+#define SP_AT(S)                                                                             \
+  {                                                                                          \
+    if (stage == 0 && cs <= (S)) {                                                           \
+      if (tid == 0) s_claim[par ^ 1] = atomicAdd(p.counter, 1u);                             \
+      stage = 1;                                                                             \
+    } else if (stage == 1) { SP_NEXT_ROW(); stage = 2; }                                     \
+    else if (stage == 2) { SP_PF_STAGE1(); stage = 3; }                                      \
+    else if (stage == 3) { SP_PF_STAGE2(); stage = 4; }                                      \
+  }
+
     do {  // one row; `break` = done with it
       if (n_a <= 0) {  // empty row: counts[i] stays 0 (pre-zeroed) / status = aggregate 0; no output
         if (FUSED && tid == 0) sp_st_status(p.status + i, kStAgg);
         pf_valid = false;
-        __syncthreads();
-        SP_NEXT_ROW();
         break;
       }
+      SP_AT(0);
       const int na0 = (int)min(n_a, (int64_t)kABatch);
 
       // ---- stage the (first batch of the) A-row metadata: start/length of each B row, a_ik; number the products ----
@@ -342,7 +372,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
       const int len_c = min(len, kStageCap + 1);  // keeps the sum in range; any clamped length disables the flat path
       int P;
       const int excl = sp_block_scan(len_c, s_warp, P);
-      SP_NEXT_ROW();   // the barrier inside the scan made the ticket visible; the two rowptr_a loads are in flight
+      SP_AT(1);   // (slot 0 ticket: the barrier inside the scan made it visible; the two rowptr_a loads are in flight)
       if (tid < na0) {
         s_se[tid] = make_int2(excl, excl + len_c);
         // the 32-aligned product numbers inside [excl, excl + len): this entry is where their chunk starts
@@ -374,16 +404,17 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
             }
           }
         }
-        SP_PF_STAGE1();
+        SP_AT(2);
 #pragma unroll
         for (int u = 0; u < kFlatU; u++)
           if (cc[u] != 0xffffffffu) sp_mark(bitmap, cc[u]);
         __syncthreads();
-        SP_PF_STAGE2();
+        SP_AT(3);
 #pragma unroll
         for (int u = 0; u < kFlatU; u++)
           if (cc[u] != 0xffffffffu) sp_verify(bitmap, cc[u]);
         __syncthreads();
+        SP_AT(4);
         if (!NUMERIC) {
           int cnt = (uint32_t)tid < NCH ? sp_count_clear_chunk(bitmap, lw) : 0;
 #pragma unroll
@@ -396,6 +427,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
         // row is still ranking its products
         if (FUSED && tid == 0) sp_st_status(p.status + i, kStAgg | (unsigned long long)wc);
         __syncthreads();
+        SP_AT(5);
         // rank; every product writes (its id, its column) into the slot: the last writer owns the slot
 #pragma unroll
         for (int u = 0; u < kFlatU; u++) {
@@ -407,6 +439,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
           }
         }
         __syncthreads();
+        SP_AT(6);
         uint32_t dmask = 0;
         if (has_val) {
 #pragma unroll
@@ -422,7 +455,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
         if (FUSED && warp == 0 && wc > 0) {
           // where this row starts in the output: nnz of all earlier rows (decoupled look-back), then publish the
           // inclusive prefix for the rows behind
-          const int64_t base = sp_lookback(p.status, i, lane);
+          const int64_t base = sp_lookback(p.status, i, lane, p.dbg);
           if (lane == 0) {
             sp_st_status(p.status + i, kStPrefix | (unsigned long long)(base + wc));
             s_base = base;
@@ -434,6 +467,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
             if (dmask & (1u << u)) atomicAdd(&acc[cc[u] >> kMaxWindowLog2], pv[u]);
           __syncthreads();
         }
+        SP_AT(7);
         int64_t ob;
         if (FUSED) ob = s_base;
         else ob = p.rowptr_c[i];
@@ -454,7 +488,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
       }
 
       // ================= general row: products re-walked per pass, window by window =================
-      SP_PF_STAGE1();
+      SP_AT(2);
       int64_t win_lo = 0, win_hi = 0;  // window index range [win_lo, win_hi]
       if (multi_window) {
         // B rows are column-sorted (SparseStorage invariant): first/last entry bound the row's columns
@@ -533,7 +567,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
 #pragma unroll
         for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
         if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(p.counts + i), (unsigned long long)cnt);
-        SP_PF_STAGE2();
+        SP_AT(3);
         break;
       }
       bool skip_row = false;
@@ -549,7 +583,7 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
         if (warp == 0) {
           if (lane == 0) sp_st_status(p.status + i, kStAgg | (unsigned long long)total);
           if (total > 0) {
-            const int64_t base = sp_lookback(p.status, i, lane);
+            const int64_t base = sp_lookback(p.status, i, lane, p.dbg);
             if (lane == 0) {
               sp_st_status(p.status + i, kStPrefix | (unsigned long long)(base + total));
               s_base = base;
@@ -608,8 +642,19 @@ __global__ void __launch_bounds__(kSpThreads, MODE == SP_SYM ? 5 : (sizeof(T) ==
       }
 #undef SP_WALK
 #undef SP_COUNT_PASS
-      SP_PF_STAGE2();
+      SP_AT(3);
     } while (false);
+    // whatever part of the next-row schedule this row's path did not reach: the ticket and the row extent are
+    // mandatory, the metadata prefetch is optional (a row without it loads its metadata at its start)
+    if (stage == 0) {
+      if (tid == 0) s_claim[par ^ 1] = atomicAdd(p.counter, 1u);
+      stage = 1;
+    }
+    if (stage == 1) {
+      __syncthreads();
+      SP_NEXT_ROW();
+    }
+#undef SP_AT
 #undef SP_PF_STAGE1
 #undef SP_PF_STAGE2
 #undef SP_NEXT_ROW
@@ -739,7 +784,7 @@ extern "C" int tsb200_spspmm_symbolic(const int64_t* rowptr_a, const int64_t* co
   p.counter = (unsigned int*)(ws + L.scalars);
   p.window_bits = window_bits_for(N);
   p.log2_wpt = log2_wpt_for(p.window_bits);
-  p.status = nullptr; p.capacity = 0; p.overflow = nullptr;
+  p.status = nullptr; p.capacity = 0; p.overflow = nullptr; p.dbg = nullptr; p.claim_slot = 0;
   int rc = sp_launch<SP_SYM, float>(p, st);
   if (rc) return rc;
   size_t tb = L.cub_bytes;
@@ -773,7 +818,7 @@ extern "C" int tsb200_spspmm_numeric(const int64_t* rowptr_a, const int64_t* col
   p.counter = (unsigned int*)(ws + L.scalars);
   p.window_bits = window_bits_for(N);
   p.log2_wpt = log2_wpt_for(p.window_bits);
-  p.status = nullptr; p.capacity = 0; p.overflow = nullptr;
+  p.status = nullptr; p.capacity = 0; p.overflow = nullptr; p.dbg = nullptr; p.claim_slot = 0;
   if (val_c && dtype == TSB200_F64) return sp_launch<SP_NUM, double>(p, st);
   return sp_launch<SP_NUM, float>(p, st);
 }
@@ -829,6 +874,16 @@ extern "C" int tsb200_spspmm_fused(const int64_t* rowptr_a, const int64_t* col_a
   p.status = (unsigned long long*)(ws + L.status);
   p.capacity = capacity;
   p.overflow = (int*)(ws + L.scalars + 48);
+  p.dbg = nullptr;
+  p.claim_slot = kClaimSlotDefault;
+  if (const char* ev = getenv("TSB200_SPSPMM_CLAIM")) {  // tuning knob, 0..6
+    const int v = atoi(ev);
+    if (v >= 0 && v <= 6) p.claim_slot = v;
+  }
+  if (getenv("TSB200_SPSPMM_DEBUG")) {  // look-back statistics in scalars [64..88): steps, empty polls, look-backs
+    p.dbg = (unsigned long long*)(ws + L.scalars + 64);
+    TSB_CUDA_TRY(cudaMemsetAsync(p.dbg, 0, 24, st));
+  }
   p.window_bits = window_bits_for(N);
   p.log2_wpt = log2_wpt_for(p.window_bits);
   int rc = (val_c && dtype == TSB200_F64) ? sp_launch<SP_FUSED, double>(p, st) : sp_launch<SP_FUSED, float>(p, st);
