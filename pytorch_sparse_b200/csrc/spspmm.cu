@@ -44,7 +44,7 @@ constexpr int kFlatU = 8;                         // products per thread on the 
 constexpr int kStageCap = kFlatU * kSpThreads;    // output entries staged in shared memory per row (2048)
 constexpr int kMaxWindowLog2 = 18;
 constexpr int kMaxWindowBits = 1 << kMaxWindowLog2;
-constexpr int kClaimSlotDefault = 0;              // single-pass mode: schedule slot of the next row's ticket (see the kernel)
+constexpr int kClaimSlotDefault = 3;              // single-pass mode: schedule slot of the next row's ticket (see the kernel)
 constexpr int kABatch = 128;                      // A entries staged per batch
 static_assert(kStageCap <= (1 << (32 - kMaxWindowLog2 - 1)), "owner id and column share one 32-bit word");
 

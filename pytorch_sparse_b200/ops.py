@@ -491,13 +491,16 @@ def spspmm(rowptr_a: Tensor, col_a: Tensor, val_a: Optional[Tensor], rowptr_b: T
     nnz_a, nnz_b = col_a.numel(), col_b.numel()
     rowptr_c = torch.empty(M + 1, dtype=torch.int64, device=dev)
     esize = 0 if not want_value else (8 if dtype == torch.float64 else 4)
-    mode = os.environ.get("TSB200_SPSPMM", "auto")   # auto | fused | two_phase
+    # two_phase (symbolic + numeric kernels) is the default. "fused" selects the single-pass kernel (rows placed by
+    # a decoupled look-back, outputs sized by the product bound): bit-identical structure, one kernel instead of two,
+    # but measured slower on B200 at C4 (6.2 vs 6.0 ms, profiles/r02_spspmm_single_pass.md) — kept as an option.
+    mode = os.environ.get("TSB200_SPSPMM", "two_phase")
     with _on_device(dev):
         nws = lib.tsb200_spspmm_workspace_bytes(M, Kd, N, nnz_a, nnz_b)
         ws = _workspace(nws, dev)
         st = _stream(dev)
         pin = _PinnedScalar()
-        if mode != "two_phase":
+        if mode in ("fused", "auto"):
             # single pass: output arrays sized by the number of products (an upper bound of nnz(C)); taken when that
             # bound fits comfortably into the memory still available, otherwise count first (two phases)
             check(lib.tsb200_spspmm_bound(_p(col_a), _p(rowptr_b), nnz_a, _p(ws), nws, pin.ptr(), st),
