@@ -378,12 +378,30 @@ def run_ours(args, w):
         dist.barrier()
         ms_serial = max_over_ranks(_time_cuda(step_serial, steps_g, 2))
         chunks = int(os.environ.get("TSB200_PIPE_CHUNKS", "4"))
-        pipe = PipelinedRowShardedSpMM(a_local, block=M, chunks=chunks)
+        split = os.environ.get("TSB200_PIPE_SPLIT", "feature")
+        transport = os.environ.get("TSB200_PIPE_TRANSPORT", "auto")
+        pipe = PipelinedRowShardedSpMM(a_local, block=M, chunks=chunks, split=split, transport=transport)
+        if split == "feature":   # slice-major layout on both sides (what a chain of layers keeps between steps)
+            x_in = pipe.to_sliced(x_local)
+            if pipe.transport == "peer":   # the producer writes straight into the symmetric buffers (both of them:
+                for _ in range(2):         # the steps alternate), so no staging copy is inside the step
+                    pipe.input_buffer(x_in, x_in.size(-1)).copy_(x_in)
+                    pipe._step += 1
+                pipe._step = 0
+                run_pipe = lambda: pipe.forward_sliced(pipe.input_buffer(x_in, x_in.size(-1)))
+            else:
+                run_pipe = lambda: pipe.forward_sliced(x_in)
+            as_rows = pipe.from_sliced
+        else:
+            run_pipe = lambda: pipe(x_local)
+            as_rows = lambda t: t
         dist.barrier()
-        ms_pipe = max_over_ranks(_time_cuda(lambda: pipe(x_local), steps_g, 2))
-        out_pipe = pipe(x_local)
+        ms_pipe = max_over_ranks(_time_cuda(run_pipe, steps_g, 2))
+        out_pipe = as_rows(run_pipe())
         multi = {"gather_ms": max_over_ranks(gather_ms), "ms_per_step_incl_gather_serial": ms_serial,
-                 "ms_per_step_incl_gather_pipelined": ms_pipe, "pipeline_chunks": chunks,
+                 "ms_per_step_incl_gather_pipelined": ms_pipe, "pipeline_chunks": chunks, "pipeline_split": split,
+                 "pipeline_transport": pipe.transport + (" (cudaMemcpyAsync pulls over NVLink from symmetric memory, "
+                                                         "copy engines only)" if pipe.transport == "peer" else ""),
                  "steps": steps_g, "collective": "NCCL all_gather_into_tensor over NVLink, inside the timed step"}
 
     # ---- parity of the timed results against the oracle (outside the timed regions), every rank ----

@@ -11,11 +11,10 @@ Two ways to make X visible:
   * `RowShardedSpMM`: all-gather X once (NCCL), then any number of steps run `local_spmm` with no
     collective inside the step ("broadcast once", BASELINE north_star) — the steady state.
   * `PipelinedRowShardedSpMM`: X changes every step (chained layers), so the gather is part of the
-    step. The gather is cut into C chunks (rows [c*Mb/C, (c+1)*Mb/C) of EVERY rank's block per chunk,
-    so every NVLink stays busy in every chunk) issued back to back on NCCL's stream; A's columns are
-    split the same way once at set-up, and the SpMM of column chunk c (tsb200_spmm_fw_acc: fp32
-    partial shared by the chunks) is launched as soon as chunk c has landed — the multiply of chunk c
-    overlaps the transfer of chunks c+1.. .
+    step. The gather is cut into C chunks issued back to back on NCCL's stream (every rank contributes
+    to every chunk, so every NVLink stays busy throughout) and the SpMM of chunk c is launched as soon
+    as chunk c has landed — the multiply of chunk c overlaps the transfer of chunks c+1.. . The chunks
+    are FEATURE slices of X by default (no partial sums; see the class), column chunks of A optionally.
 """
 from __future__ import annotations
 
@@ -147,20 +146,140 @@ class PipelinedRowShardedSpMM:
     """Sum-SpMM of this rank's row block with a dense operand that is gathered INSIDE the step, chunk by chunk,
     while the chunks that have already landed are being multiplied (forward only; CUDA / NCCL).
 
-    `block` = rows of the dense operand every rank holds (all equal); `chunks` = pipeline depth."""
+    `block` = rows of the dense operand every rank holds (all equal); `chunks` = pipeline depth C.
 
-    def __init__(self, a_local: SparseTensor, block: int, chunks: int = 4, group=None):
+    split="feature" (default): the operand travels in C FEATURE slices. Slice c is all-gathered as a contiguous
+    [world * block, F / C] matrix and multiplied by the whole of A with the ordinary SpMM kernel into slice c of the
+    result — no partial sums, the only extra work is that A's index arrays are re-read C times. The fast path keeps
+    the slice-major layout on both sides (`forward_sliced`: [C, block, F/C] in, [C, M, F/C] out), which is what a
+    chain of layers wants: the output of one step is already laid out for the gather of the next.
+    split="column": A's columns are split instead (`split_column_chunks`) and the chunks share an fp32 partial
+    (tsb200_spmm_fw_acc). Measured slower — every chunk re-walks the row structure and read-modify-writes the
+    partial (profiles/r02_results.md) — kept for operands that cannot be sliced by features.
+
+    transport="peer" (default on CUDA/NCCL groups): every rank keeps its slices in a symmetric-memory buffer and PULLS
+    the peers' slices with cudaMemcpyAsync over NVLink — copy engines only. The SpMM kernel is a persistent grid that
+    fills every SM, so a transfer that needs SMs (NCCL's all-gather kernel) cannot run beside it and the "overlap"
+    serialises; DMA pulls do overlap (profiles/r02_results.md). transport="nccl": chunked all_gather_into_tensor."""
+
+    def __init__(self, a_local: SparseTensor, block: int, chunks: int = 4, group=None, split: str = "feature",
+                 transport: str = "auto"):
+        assert split in ("feature", "column") and transport in ("auto", "peer", "nccl")
+        if transport == "auto":   # peer-memory copies need CUDA tensors and the symmetric-memory allocator
+            transport = "peer" if (a_local.is_cuda() and split == "feature" and _world(group) > 1
+                                   and dist.get_backend(group) == "nccl") else "nccl"
+        self.transport = transport
         self.group = group
         self.world = _world(group)
         self.block = block
         self.chunks = chunks
+        self.split = split
         rowptr, col, value = a_local.csr()
         assert a_local.sparse_size(1) == self.world * block
         self.M = a_local.sparse_size(0)
-        self.parts, self.mc = split_column_chunks(rowptr, col, value, block, self.world, chunks)
+        self.csr = (rowptr, col, value)
+        if split == "column":
+            self.parts, self.mc = split_column_chunks(rowptr, col, value, block, self.world, chunks)
         self._x = None
         self._partial = None
 
+    # ------------------------------------------------------------------ feature slices
+    def to_sliced(self, x: Tensor) -> Tensor:
+        """[rows, F] -> slice-major [C, rows, F / C]."""
+        rows, F = x.shape
+        assert F % self.chunks == 0
+        return x.view(rows, self.chunks, F // self.chunks).permute(1, 0, 2).contiguous()
+
+    @staticmethod
+    def from_sliced(xs: Tensor) -> Tensor:
+        """slice-major [C, rows, Fc] -> [rows, C * Fc]."""
+        C, rows, Fc = xs.shape
+        return xs.permute(1, 0, 2).reshape(rows, C * Fc)
+
+    # ---- transport 1: copy engines over peer memory (torch symmetric memory), no SM is used by the transfer ----
+    def _peer_setup(self, like: Tensor, Fc: int):
+        """Collective. Two symmetric input buffers (alternating steps) + views of every peer's buffers."""
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._sym, self._hdl, self._peer = [], [], []
+        for _ in range(2):
+            buf = symm.empty((self.chunks, self.block, Fc), dtype=like.dtype, device=like.device)
+            hdl = symm.rendezvous(buf, group)
+            self._sym.append(buf)
+            self._hdl.append(hdl)
+            self._peer.append([hdl.get_buffer(r, (self.chunks, self.block, Fc), like.dtype)
+                               for r in range(self.world)])
+        self._copy_streams = [torch.cuda.Stream(device=like.device) for _ in range(self.world)]
+        self._step = 0
+
+    def input_buffer(self, like: Tensor, Fc: int) -> Tensor:
+        """The symmetric [C, block, Fc] buffer the NEXT step will be gathered from: a producer that writes its slices
+        straight into it saves the staging copy `forward_sliced` would otherwise make."""
+        if getattr(self, "_sym", None) is None or self._sym[0].dtype != like.dtype or self._sym[0].size(-1) != Fc:
+            self._peer_setup(like, Fc)
+        return self._sym[self._step & 1]
+
+    def _gather_peer(self, x_sliced: Tensor, xg: Tensor):
+        """Pull every peer's slices with cudaMemcpyAsync over NVLink (one copy stream per peer, copy engines only),
+        slice by slice; returns per-slice lists of events the compute stream waits on."""
+        C, Fc = self.chunks, x_sliced.size(-1)
+        mine = self.input_buffer(x_sliced, Fc)
+        if x_sliced.data_ptr() != mine.data_ptr():
+            mine.copy_(x_sliced)
+        k = self._step & 1
+        self._step += 1
+        # every rank has written buffer k and is done with the step that last read buffer k
+        self._hdl[k].barrier()
+        me = _rank(self.group)
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        events = [[] for _ in range(C)]
+        for r in range(self.world):
+            if r == me:
+                continue
+            st = self._copy_streams[r]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                for c in range(C):
+                    xg[c, r * self.block:(r + 1) * self.block].copy_(self._peer[k][r][c], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    events[c].append(ev)
+        for c in range(C):   # own rows: a local copy on the compute stream
+            xg[c, me * self.block:(me + 1) * self.block].copy_(mine[c], non_blocking=True)
+        return events
+
+    def forward_sliced(self, x_sliced: Tensor) -> Tensor:
+        """x_sliced [C, block, Fc] (this rank's rows of every feature slice) -> [C, M, Fc]."""
+        C, rows, Fc = x_sliced.shape
+        assert C == self.chunks and rows == self.block and x_sliced.is_contiguous()
+        if self._x is None or self._x.dtype != x_sliced.dtype or self._x.size(-1) != Fc:
+            self._x = x_sliced.new_empty((C, self.world * self.block, Fc))
+        xg = self._x
+        works, events = [], None
+        if self.world > 1 and self.transport == "peer":
+            events = self._gather_peer(x_sliced, xg)
+        else:
+            for c in range(C):
+                if self.world > 1:
+                    works.append(dist.all_gather_into_tensor(xg[c], x_sliced[c], group=self.group, async_op=True))
+                else:
+                    xg[c].copy_(x_sliced[c])
+        rowptr, col, value = self.csr
+        value = None if value is None else value.to(x_sliced.dtype)
+        out = []
+        for c in range(C):
+            if works:
+                works[c].wait()          # the compute stream waits for slice c only
+            if events is not None:
+                cur = torch.cuda.current_stream()
+                for ev in events[c]:
+                    cur.wait_event(ev)
+            out.append(ops.spmm_fw(rowptr, col, value, xg[c], "sum")[0])
+        return torch.stack(out, dim=0)
+
+    # ------------------------------------------------------------------ column chunks
     def _buffers(self, x_local: Tensor):
         F = x_local.size(1)
         if self._x is None or self._x.dtype != x_local.dtype or self._x.size(-1) != F:
@@ -168,8 +287,7 @@ class PipelinedRowShardedSpMM:
             self._partial = torch.empty((self.M, F), dtype=torch.float32, device=x_local.device)
         return self._x, self._partial
 
-    def __call__(self, x_local: Tensor) -> Tensor:
-        assert x_local.dim() == 2 and x_local.size(0) == self.block and x_local.is_contiguous()
+    def _forward_columns(self, x_local: Tensor) -> Tensor:
         xg, partial = self._buffers(x_local)
         mc, C = self.mc, self.chunks
         works = []
@@ -191,3 +309,11 @@ class PipelinedRowShardedSpMM:
                 return ops.spmm_fw(rp, cl, v, x_flat, "sum")[0]
             ops.spmm_fw_acc(rp, cl, v, x_flat, partial, out, mode)
         return out
+
+    def __call__(self, x_local: Tensor) -> Tensor:
+        """x_local [block, F] -> [M, F] (row-major on both sides; the feature split converts the layout on the way
+        in and out — use `forward_sliced` to keep the slice-major layout across steps)."""
+        assert x_local.dim() == 2 and x_local.size(0) == self.block and x_local.is_contiguous()
+        if self.split == "column":
+            return self._forward_columns(x_local)
+        return self.from_sliced(self.forward_sliced(self.to_sliced(x_local)))

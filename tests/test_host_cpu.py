@@ -191,10 +191,13 @@ N = world * block
 dense = ((torch.rand(world * M, N, generator=g) < 0.15).float() * torch.randn(world * M, N, generator=g))
 x = torch.randn(N, K, generator=g)
 a_local = ts.SparseTensor.from_dense(dense[rank * M:(rank + 1) * M])
-pipe = PipelinedRowShardedSpMM(a_local, block=block, chunks=C)
-for _ in range(2):                           # buffers are reused across steps
-    y = pipe(x[rank * block:(rank + 1) * block].contiguous())
-    assert torch.allclose(y, (dense @ x)[rank * M:(rank + 1) * M], atol=1e-4), "pipelined shard mismatch"
+for split in ("feature", "column"):
+    pipe = PipelinedRowShardedSpMM(a_local, block=block, chunks=C, split=split)
+    for _ in range(2):                           # buffers are reused across steps
+        y = pipe(x[rank * block:(rank + 1) * block].contiguous())
+        assert torch.allclose(y, (dense @ x)[rank * M:(rank + 1) * M], atol=1e-4), f"pipelined ({split}) shard mismatch"
+xs = pipe.to_sliced(x[rank * block:(rank + 1) * block].contiguous())
+assert torch.equal(pipe.from_sliced(xs), x[rank * block:(rank + 1) * block])
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
