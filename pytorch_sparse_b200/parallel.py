@@ -18,6 +18,7 @@ Two ways to make X visible:
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -169,6 +170,9 @@ class PipelinedRowShardedSpMM:
             transport = "peer" if (a_local.is_cuda() and split == "feature" and _world(group) > 1
                                    and dist.get_backend(group) == "nccl") else "nccl"
         self.transport = transport
+        # concurrent DMA streams of the pulls: ONE is fastest at N = 8 (3.39 ms vs 5.78 / 4.91 ms with 2 / 7 streams:
+        # concurrent peer copies contend), and as fast as any at N = 2 (profiles/r02_results.md)
+        self.peer_streams = int(os.environ.get("TSB200_PEER_STREAMS", "1"))
         self.group = group
         self.world = _world(group)
         self.block = block
@@ -235,17 +239,21 @@ class PipelinedRowShardedSpMM:
         ready = torch.cuda.Event()
         ready.record(cur)
         events = [[] for _ in range(C)]
-        for r in range(self.world):
-            if r == me:
-                continue
-            st = self._copy_streams[r]
+        # Peer order is staggered by rank (at hop h every rank pulls from rank me + h: a permutation, so no source
+        # serves two pullers in the same hop) and spread round-robin over `peer_streams` copy streams.
+        ns = max(1, min(self.peer_streams, self.world - 1))
+        for st in self._copy_streams[:ns]:
             st.wait_event(ready)
-            with torch.cuda.stream(st):
-                for c in range(C):
+        for c in range(C):
+            for h in range(1, self.world):
+                r = (me + h) % self.world
+                st = self._copy_streams[(h - 1) % ns]
+                with torch.cuda.stream(st):
                     xg[c, r * self.block:(r + 1) * self.block].copy_(self._peer[k][r][c], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    events[c].append(ev)
+            for st in self._copy_streams[:ns]:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events[c].append(ev)
         for c in range(C):   # own rows: a local copy on the compute stream
             xg[c, me * self.block:(me + 1) * self.block].copy_(mine[c], non_blocking=True)
         return events

@@ -272,3 +272,53 @@ def test_full_size_c3_max_vs_oracle(oracle):
     bv, bm = oracle.spmm_minmax_bw(col, value.double().abs(), x.double().abs(), go.double().abs(), rarg)
     assert ((gv.cpu().double() - rv).abs() <= 1e-5 * bv + 1e-30).all()
     assert ((gm.cpu().double() - rm).abs() <= 1e-5 * bm + 1e-30).all()
+
+
+@pytest.mark.parametrize("dtype,K", [(torch.float32, 64), (torch.bfloat16, 128), (torch.float16, 32)])
+@pytest.mark.parametrize("P", [2, 3])
+def test_column_block_accumulate_modes_vs_oracle(oracle, dtype, K, P):
+    """tsb200_spmm_fw_acc: a SUM SpMM assembled from P column blocks through the fp32 partial (first / middle / last
+    block modes), on a power-law matrix whose long rows go through the segment queue and the combine kernel —
+    against the oracle's single pass on the same inputs."""
+    from pytorch_sparse_b200.parallel import split_column_chunks
+    M, N = 3000, 3 * 1024
+    row, rowptr, col = random_csr(M, N, 12, seed=5, power_law=True, empty_rows=(0, 7, 2999),
+                                  long_rows=[(3, 3000), (4, 700), (5, 257), (6, 256)])
+    g = torch.Generator().manual_seed(6)
+    value = torch.randn(col.numel(), generator=g).to(dtype)
+    x = torch.randn(N, K, generator=g).to(dtype)
+    parts, _ = split_column_chunks(rowptr.to(DEV), col.to(DEV), value.to(DEV), N, 1, P)   # world = 1: ids unchanged
+    partial = torch.empty(M, K, dtype=torch.float32, device=DEV)
+    out = torch.empty(M, K, dtype=dtype, device=DEV)
+    xd = x.to(DEV)
+    for c, (rp, cl, v) in enumerate(parts):
+        ops.spmm_fw_acc(rp, cl, v, xd, partial, out, 1 if c == 0 else (3 if c == P - 1 else 2))
+    ref, _ = oracle.spmm(rowptr, col, value.float(), x.float(), "sum")
+    bound, _ = oracle.spmm(rowptr, col, value.float().abs(), x.float().abs(), "sum")
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert ((out.cpu().float() - ref).abs() <= tol * bound + 1e-30).all()
+    single, _ = ops.spmm_fw(rowptr.to(DEV), col.to(DEV), value.to(DEV), xd, "sum")
+    assert ((out.float() - single.float()).abs().cpu() <= tol * bound + 1e-30).all()
+
+
+@pytest.mark.parametrize("split", ["feature", "column"])
+def test_pipelined_row_sharded_spmm_single_rank(oracle, split):
+    """PipelinedRowShardedSpMM on one rank (the gather degenerates to local copies): both splits reproduce the
+    plain SpMM; the slice-major fast path round-trips."""
+    from pytorch_sparse_b200.parallel import PipelinedRowShardedSpMM
+    M = N = 2048
+    row, rowptr, col = random_csr(M, N, 9, seed=11, empty_rows=(1,), long_rows=[(2, 600)])
+    g = torch.Generator().manual_seed(12)
+    value = torch.randn(col.numel(), generator=g).bfloat16()
+    x = torch.randn(N, 128, generator=g).bfloat16()
+    a = ts.SparseTensor(rowptr=rowptr.to(DEV), col=col.to(DEV), value=value.to(DEV), sparse_sizes=(M, N),
+                        is_sorted=True, trust_data=True)
+    pipe = PipelinedRowShardedSpMM(a, block=N, chunks=4, split=split)
+    y = pipe(x.to(DEV))
+    ref, _ = oracle.spmm(rowptr, col, value.float(), x.float(), "sum")
+    bound, _ = oracle.spmm(rowptr, col, value.float().abs(), x.float().abs(), "sum")
+    assert ((y.cpu().float() - ref).abs() <= 1e-2 * bound + 1e-30).all()
+    if split == "feature":
+        xs = pipe.to_sliced(x.to(DEV))
+        assert torch.equal(pipe.from_sliced(xs).cpu(), x)
+        assert torch.equal(pipe.from_sliced(pipe.forward_sliced(xs)), y)
