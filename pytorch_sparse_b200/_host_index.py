@@ -6,8 +6,6 @@ PyTorch index ops. This is construction convenience only — every arithmetic op
 path (spmm, value gradients, coalesce reductions, spspmm) exists solely as a CUDA kernel in
 libtsb200 and raises for CPU tensors.
 """
-from __future__ import annotations
-
 from typing import Optional, Tuple
 
 import torch

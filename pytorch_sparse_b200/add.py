@@ -3,8 +3,6 @@
 sum", so they ride on the native coalesce kernels. `narrow` slices rows (pointer arithmetic) or columns
 (torch_sparse/narrow.py:8-77). `mul` / `mul_` / `mul_nnz` and the dense-vector `add` variants
 (torch_sparse/mul.py, add.py:21-37, 59-104) complete the row/column scaling family."""
-from __future__ import annotations
-
 from typing import Optional
 
 import torch
@@ -30,29 +28,46 @@ def _broadcast_to_nnz(src: SparseTensor, other: Tensor) -> Tensor:
         return other.squeeze(1)[src.storage.row()]
     if other.dim() >= 2 and other.size(0) == 1 and other.size(1) == src.size(1):
         return other.squeeze(0)[src.storage.col()]
-    raise ValueError(f"Size mismatch: Expected size ({src.size(0)}, 1, ...) or (1, {src.size(1)}, ...), "
-                     f"but got size {other.size()}.")
+    raise ValueError("Size mismatch: Expected size (" + str(src.size(0)) + ", 1, ...) or (1, " + str(src.size(1)) +
+                     ", ...), but got size " + str(other.size()) + ".")
 
 
-def add(src: SparseTensor, other) -> SparseTensor:
+@torch.jit._overload  # noqa: F811
+def add(src, other):  # noqa: F811
+    # type: (SparseTensor, Tensor) -> SparseTensor
+    pass
+
+
+@torch.jit._overload  # noqa: F811
+def add(src, other):  # noqa: F811
+    # type: (SparseTensor, SparseTensor) -> SparseTensor
+    pass
+
+
+def add(src, other):  # noqa: F811
     """sparse + dense row/column vector (values shifted per row / column; a value-less tensor counts as ones) or
-    sparse + sparse (concatenate + native coalesce with sum) — torch_sparse/add.py:21-56."""
+    sparse + sparse (concatenate + native coalesce with sum) — torch_sparse/add.py:21-56. TorchScript-compatible."""
     if isinstance(other, Tensor):
         term = _broadcast_to_nnz(src, other)
         value = src.storage.value()
-        value = term + 1 if value is None else term.to(value.dtype) + value
+        if value is None:
+            value = term + 1
+        else:
+            value = term.to(value.dtype) + value
         return src.set_value(value, layout="coo")
-    if not isinstance(other, SparseTensor):
+    elif isinstance(other, SparseTensor):
+        rowA, colA, valueA = src.coo()
+        rowB, colB, valueB = other.coo()
+        value: Optional[Tensor] = None
+        if valueA is not None and valueB is not None:
+            value = torch.cat([valueA, valueB], dim=0)
+        M = max(src.size(0), other.size(0))
+        N = max(src.size(1), other.size(1))
+        row, col, value = torch.ops.tsb200.coalesce(torch.cat([rowA, rowB]), torch.cat([colA, colB]), value, M, N,
+                                                    "sum")
+        return SparseTensor(row, None, col, value, (M, N), True, True)
+    else:
         raise NotImplementedError
-    rowA, colA, valueA = src.coo()
-    rowB, colB, valueB = other.coo()
-    value: Optional[Tensor] = None
-    if valueA is not None and valueB is not None:
-        value = torch.cat([valueA, valueB], dim=0)
-    M = max(src.size(0), other.size(0))
-    N = max(src.size(1), other.size(1))
-    row, col, value = ops.coalesce(torch.cat([rowA, rowB]), torch.cat([colA, colB]), value, M, N, "sum")
-    return SparseTensor(row=row, col=col, value=value, sparse_sizes=(M, N), is_sorted=True, trust_data=True)
 
 
 def add_(src: SparseTensor, other: Tensor) -> SparseTensor:
@@ -120,17 +135,30 @@ def narrow(src: SparseTensor, dim: int, start: int, length: int) -> SparseTensor
 SparseTensor.narrow = lambda self, dim, start, length: narrow(self, dim, start, length)
 
 
-def mul(src: SparseTensor, other) -> SparseTensor:
+@torch.jit._overload  # noqa: F811
+def mul(src, other):  # noqa: F811
+    # type: (SparseTensor, Tensor) -> SparseTensor
+    pass
+
+
+@torch.jit._overload  # noqa: F811
+def mul(src, other):  # noqa: F811
+    # type: (SparseTensor, SparseTensor) -> SparseTensor
+    pass
+
+
+def mul(src, other):  # noqa: F811
     """Scale the stored values row-wise (`other` of shape [M, 1]) or column-wise ([1, N]) — the GCN
     normalisation step either side of SpMM — or multiply two coalesced SparseTensors entry-wise (the result
     keeps the positions stored in BOTH operands): torch_sparse/mul.py:22-79. Structure and caches of the
-    dense-operand branch are shared with `src`."""
+    dense-operand branch are shared with `src`. TorchScript-compatible."""
     if isinstance(other, Tensor):
         factor = _broadcast_to_nnz(src, other)
         value = src.storage.value()
-        return src.set_value(factor if value is None else factor.to(value.dtype) * value, layout="coo")
-    if not isinstance(other, SparseTensor):
-        raise NotImplementedError
+        if value is not None:
+            factor = factor.to(value.dtype) * value
+        return src.set_value(factor, layout="coo")
+    assert isinstance(other, SparseTensor)
     if not src.is_coalesced():
         raise ValueError("The `src` tensor is not coalesced")
     if not other.is_coalesced():
@@ -143,15 +171,14 @@ def mul(src: SparseTensor, other) -> SparseTensor:
     row, col, value = torch.cat([rowA, rowB]), torch.cat([colA, colB]), torch.cat([valueA, valueB], dim=0)
     # native stable (row, col) sort of the concatenation: a position stored in both operands shows up as two
     # neighbours, A's entry first
-    perm = ops.sort_perm(row, col, M, N)
+    perm = torch.ops.tsb200.sort_perm(row, col, M, N)
     if perm is not None:
         row, col, value = row[perm], col[perm], value[perm]
     if row.numel() < 2:
         both = torch.zeros(0, dtype=torch.long, device=row.device)
     else:
         both = ((row[1:] == row[:-1]) & (col[1:] == col[:-1])).nonzero().view(-1) + 1
-    return SparseTensor(row=row[both], col=col[both], value=value[both - 1] * value[both], sparse_sizes=(M, N),
-                        is_sorted=True, trust_data=True)
+    return SparseTensor(row[both], None, col[both], value[both - 1] * value[both], (M, N), True, True)
 
 
 def mul_(src: SparseTensor, other: Tensor) -> SparseTensor:

@@ -3,38 +3,78 @@
 API-compatible with `torch_sparse.storage.SparseStorage` (torch_sparse/storage.py:20-801): same
 constructor arguments, the same private attribute names (`_row`, `_rowptr`, `_col`, `_value`,
 `_rowcount`, `_colptr`, `_colcount`, `_csr2csc`, `_csc2csr`) that `matmul.py` and the reference's
-tests read, and the same lazy-cache semantics. Differences, all on the GPU side:
+tests read, the same lazy-cache semantics, and — like the reference's — a TorchScript class
+(`@torch.jit.script`, torch_sparse/storage.py:21): every native step is a registered operator
+(`torch.ops.tsb200.*`, torch_ops.py), so scripted code can build and use storages. Differences, all on
+the GPU side:
   * sort-on-construct, csr2csc/colptr and coalesce run as fused libtsb200 kernels
     (one stable radix sort over only the significant key bits, no E-sized int64 temporaries),
-  * `trust_data=True` (or CUDA tensors + explicit sizes) skips the host-synchronising bound checks.
+  * `trust_data=True` (or CUDA tensors + explicit sizes) skips the host-synchronising bound checks,
+  * `_row_csc` (= row[csr2csc], the column array of the transposed CSR view) is kept as an extra cache.
+CPU tensors are accepted for CONSTRUCTION only (index bookkeeping in _host_index.py); all arithmetic is CUDA.
 """
-from __future__ import annotations
-
 from typing import List, Optional, Tuple
 
 import torch
 from torch import Tensor
 
 from . import _host_index as host
-from . import ops
-
-_CACHE_KEYS = ("rowcount", "colptr", "colcount", "csr2csc", "csc2csr")
+from . import torch_ops  # noqa: F401  (the operators below must be registered before this class is compiled)
 
 
-def _long_vector(t: Optional[Tensor], name: str, numel: Optional[int], device) -> Optional[Tensor]:
+def _vetted(t: Optional[Tensor], what: str, numel: int, like: Tensor) -> Optional[Tensor]:
+    """An optional int64 index vector of `numel` entries (-1: any length) on the device of `like`."""
     if t is None:
         return None
-    assert t.dtype == torch.long, f"{name} must be int64"
-    assert t.dim() == 1, f"{name} must be 1-dimensional"
-    assert t.device == device, f"{name} lives on {t.device}, expected {device}"
-    if numel is not None:
-        assert t.numel() == numel, f"{name} has {t.numel()} entries, expected {numel}"
+    assert t.dtype == torch.long, what + " must be int64"
+    assert t.dim() == 1, what + " must be 1-dimensional"
+    assert t.device == like.device, what + " lives on another device than col"
+    if numel >= 0:
+        assert t.numel() == numel, what + " has the wrong number of entries"
     return t.contiguous()
 
 
-class SparseStorage:
-    __slots__ = ("_row", "_rowptr", "_col", "_value", "_sparse_sizes", "_rowcount", "_colptr", "_colcount",
-                 "_csr2csc", "_csc2csr", "_row_csc")
+def _moved(t: Optional[Tensor], how: int, device: torch.device, non_blocking: bool) -> Optional[Tensor]:
+    """how: 0 = clone, 1 = move to `device`, 2 = pin."""
+    if t is None:
+        return None
+    if how == 0:
+        return t.clone()
+    if how == 1:
+        return t.to(device, non_blocking=non_blocking)
+    return t.pin_memory()
+
+
+def _resized(ptr: Optional[Tensor], count: Optional[Tensor], old: int, new: int,
+             nnz: int) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """Pointer / count vectors of one sparse dimension after growing or shrinking it from `old` to `new`."""
+    d = new - old
+    if d > 0:
+        if ptr is not None:
+            ptr = torch.cat([ptr, ptr.new_full((d,), nnz)])
+        if count is not None:
+            count = torch.cat([count, count.new_zeros(d)])
+    elif d < 0:
+        if ptr is not None:
+            ptr = ptr[:d]
+        if count is not None:
+            count = count[:d]
+    return ptr, count
+
+
+@torch.jit.script
+class SparseStorage(object):
+    _row: Optional[Tensor]
+    _rowptr: Optional[Tensor]
+    _col: Tensor
+    _value: Optional[Tensor]
+    _sparse_sizes: Tuple[int, int]
+    _rowcount: Optional[Tensor]
+    _colptr: Optional[Tensor]
+    _colcount: Optional[Tensor]
+    _csr2csc: Optional[Tensor]
+    _csc2csr: Optional[Tensor]
+    _row_csc: Optional[Tensor]
 
     def __init__(self, row: Optional[Tensor] = None, rowptr: Optional[Tensor] = None,
                  col: Optional[Tensor] = None, value: Optional[Tensor] = None,
@@ -44,104 +84,121 @@ class SparseStorage:
                  csc2csr: Optional[Tensor] = None, is_sorted: bool = False, trust_data: bool = False):
         assert row is not None or rowptr is not None
         assert col is not None
-        dev = col.device
-        col = _long_vector(col, "col", None, dev)
-        E = col.numel()
+        col_v = _vetted(col, "col", -1, col)
+        assert col_v is not None
+        E = col_v.numel()
 
-        m_hint = None if sparse_sizes is None else sparse_sizes[0]
-        n_hint = None if sparse_sizes is None else sparse_sizes[1]
+        m_hint: Optional[int] = None
+        n_hint: Optional[int] = None
+        if sparse_sizes is not None:
+            m_hint = sparse_sizes[0]
+            n_hint = sparse_sizes[1]
+        M = 0
         if m_hint is None:
             if rowptr is not None:
                 M = rowptr.numel() - 1
-            else:
-                M = int(row.max()) + 1 if E > 0 else 0
+            elif row is not None and E > 0:
+                M = int(row.max()) + 1
         else:
-            M = int(m_hint)
+            M = m_hint
             if rowptr is not None:
                 assert rowptr.numel() - 1 == M
-            elif E > 0 and not trust_data:
+            elif row is not None and E > 0 and not trust_data:
                 assert int(row.max()) < M
+        N = 0
         if n_hint is None:
-            N = int(col.max()) + 1 if E > 0 else 0
+            if E > 0:
+                N = int(col_v.max()) + 1
         else:
-            N = int(n_hint)
+            N = n_hint
             if E > 0 and not trust_data:
-                assert int(col.max()) < N
+                assert int(col_v.max()) < N
 
-        self._row = _long_vector(row, "row", E, dev)
-        self._rowptr = _long_vector(rowptr, "rowptr", M + 1, dev)
-        self._col = col
         if value is not None:
-            assert value.device == dev
+            assert value.device == col_v.device
             assert value.size(0) == E
             value = value.contiguous()
+        self._row = _vetted(row, "row", E, col_v)
+        self._rowptr = _vetted(rowptr, "rowptr", M + 1, col_v)
+        self._col = col_v
         self._value = value
         self._sparse_sizes = (M, N)
-        self._rowcount = _long_vector(rowcount, "rowcount", M, dev)
-        self._colptr = _long_vector(colptr, "colptr", N + 1, dev)
-        self._colcount = _long_vector(colcount, "colcount", N, dev)
-        self._csr2csc = _long_vector(csr2csc, "csr2csc", E, dev)
-        self._csc2csr = _long_vector(csc2csr, "csc2csr", E, dev)
-        self._row_csc = None  # row[csr2csc]: derived view for the SpMM backward, not one of the reference's cache keys
+        self._rowcount = _vetted(rowcount, "rowcount", M, col_v)
+        self._colptr = _vetted(colptr, "colptr", N + 1, col_v)
+        self._colcount = _vetted(colcount, "colcount", N, col_v)
+        self._csr2csc = _vetted(csr2csc, "csr2csc", E, col_v)
+        self._csc2csr = _vetted(csc2csr, "csc2csr", E, col_v)
+        row_csc: Optional[Tensor] = None  # row[csr2csc]: derived view for the SpMM backward, not a reference cache key
+        self._row_csc = row_csc
 
         if not is_sorted and E > 1:
             self._sort_()
 
     # ------------------------------------------------------------------ construction helpers
-    def _sort_(self) -> None:
+    def _sort_(self):
         """Bring the entries into row-major order (torch_sparse/storage.py:149-162)."""
         M, N = self._sparse_sizes
         row = self.row()
+        perm: Optional[Tensor] = None
         if self._col.is_cuda:
-            perm = ops.sort_perm(row, self._col, M, N)
+            perm = torch.ops.tsb200.sort_perm(row, self._col, M, N)
         else:
             perm = host.sort_perm(row, self._col, N)
-        if perm is None:
-            return
-        self._row = row[perm]
-        self._rowptr = None
-        self._col = self._col[perm]
-        if self._value is not None:
-            self._value = self._value[perm]
-        self._csr2csc = None
-        self._csc2csr = None
-        self._row_csc = None
+        if perm is not None:
+            self._row = row[perm]
+            self._rowptr = None
+            self._col = self._col[perm]
+            value = self._value
+            if value is not None:
+                self._value = value[perm]
+            self._csr2csc = None
+            self._csc2csr = None
+            self._row_csc = None
 
     @classmethod
-    def empty(cls) -> "SparseStorage":
+    def empty(self):
         z = torch.empty(0, dtype=torch.long)
-        return cls(row=z, col=z.clone(), sparse_sizes=(0, 0), is_sorted=True, trust_data=True)
+        return SparseStorage(z, None, z.clone(), None, (0, 0), None, None, None, None, None, True, True)
 
-    def _replace(self, **kw) -> "SparseStorage":
-        """New storage sharing all tensors except the ones overridden in `kw`."""
-        fields = dict(row=self._row, rowptr=self._rowptr, col=self._col, value=self._value,
-                      sparse_sizes=self._sparse_sizes, rowcount=self._rowcount, colptr=self._colptr,
-                      colcount=self._colcount, csr2csc=self._csr2csc, csc2csr=self._csc2csr)
-        fields.update(kw)
-        return SparseStorage(is_sorted=True, trust_data=True, **fields)
+    def _with(self, row: Optional[Tensor], rowptr: Optional[Tensor], col: Tensor, value: Optional[Tensor],
+              sparse_sizes: Tuple[int, int], rowcount: Optional[Tensor], colptr: Optional[Tensor],
+              colcount: Optional[Tensor], csr2csc: Optional[Tensor], csc2csr: Optional[Tensor]):
+        """A storage over already ordered, already validated pieces."""
+        return SparseStorage(row, rowptr, col, value, (sparse_sizes[0], sparse_sizes[1]), rowcount, colptr, colcount,
+                             csr2csc, csc2csr, True, True)
 
     # ------------------------------------------------------------------ COO / CSR views
     def has_row(self) -> bool:
         return self._row is not None
 
     def row(self) -> Tensor:
-        if self._row is None:
-            if self._rowptr is None:
+        row = self._row
+        if row is None:
+            rowptr = self._rowptr
+            if rowptr is None:
                 raise ValueError
-            fn = ops.ptr2ind if self._rowptr.is_cuda else host.ptr2ind
-            self._row = fn(self._rowptr, self._col.numel())
-        return self._row
+            if rowptr.is_cuda:
+                row = torch.ops.tsb200.ptr2ind(rowptr, self._col.numel())
+            else:
+                row = host.ptr2ind(rowptr, self._col.numel())
+            self._row = row
+        return row
 
     def has_rowptr(self) -> bool:
         return self._rowptr is not None
 
     def rowptr(self) -> Tensor:
-        if self._rowptr is None:
-            if self._row is None:
+        rowptr = self._rowptr
+        if rowptr is None:
+            row = self._row
+            if row is None:
                 raise ValueError
-            fn = ops.ind2ptr if self._row.is_cuda else host.ind2ptr
-            self._rowptr = fn(self._row, self._sparse_sizes[0])
-        return self._rowptr
+            if row.is_cuda:
+                rowptr = torch.ops.tsb200.ind2ptr(row, self._sparse_sizes[0])
+            else:
+                rowptr = host.ind2ptr(row, self._sparse_sizes[0])
+            self._rowptr = rowptr
+        return rowptr
 
     def col(self) -> Tensor:
         return self._col
@@ -155,18 +212,21 @@ class SparseStorage:
     def _checked_value(self, value: Optional[Tensor], layout: Optional[str]) -> Optional[Tensor]:
         if value is None:
             return None
-        if layout == "csc":
+        if layout is not None and layout == "csc":
             value = value[self.csc2csr()]
         assert value.device == self._col.device
         assert value.size(0) == self._col.numel()
         return value.contiguous()
 
-    def set_value_(self, value: Optional[Tensor], layout: Optional[str] = None) -> "SparseStorage":
+    def set_value_(self, value: Optional[Tensor], layout: Optional[str] = None):
         self._value = self._checked_value(value, layout)
         return self
 
-    def set_value(self, value: Optional[Tensor], layout: Optional[str] = None) -> "SparseStorage":
-        return self._replace(value=self._checked_value(value, layout))
+    def set_value(self, value: Optional[Tensor], layout: Optional[str] = None):
+        out = self._with(self._row, self._rowptr, self._col, self._checked_value(value, layout), self._sparse_sizes,
+                         self._rowcount, self._colptr, self._colcount, self._csr2csc, self._csc2csr)
+        out._row_csc = self._row_csc
+        return out
 
     def sparse_sizes(self) -> Tuple[int, int]:
         return self._sparse_sizes
@@ -174,28 +234,15 @@ class SparseStorage:
     def sparse_size(self, dim: int) -> int:
         return self._sparse_sizes[dim]
 
-    def sparse_resize(self, sparse_sizes: Tuple[int, int]) -> "SparseStorage":
+    def sparse_resize(self, sparse_sizes: Tuple[int, int]):
         assert len(sparse_sizes) == 2
-        (M0, N0), nnz = self._sparse_sizes, self._col.numel()
+        nnz = self._col.numel()
+        rowptr, rowcount = _resized(self._rowptr, self._rowcount, self._sparse_sizes[0], sparse_sizes[0], nnz)
+        colptr, colcount = _resized(self._colptr, self._colcount, self._sparse_sizes[1], sparse_sizes[1], nnz)
+        return self._with(self._row, rowptr, self._col, self._value, sparse_sizes, rowcount, colptr, colcount,
+                          self._csr2csc, self._csc2csr)
 
-        def _grow(ptr, count, old, new):
-            d = new - old
-            if d > 0:
-                if ptr is not None:
-                    ptr = torch.cat([ptr, ptr.new_full((d,), nnz)])
-                if count is not None:
-                    count = torch.cat([count, count.new_zeros(d)])
-            elif d < 0:
-                ptr = None if ptr is None else ptr[:d]
-                count = None if count is None else count[:d]
-            return ptr, count
-
-        rowptr, rowcount = _grow(self._rowptr, self._rowcount, M0, sparse_sizes[0])
-        colptr, colcount = _grow(self._colptr, self._colcount, N0, sparse_sizes[1])
-        return self._replace(rowptr=rowptr, rowcount=rowcount, colptr=colptr, colcount=colcount,
-                             sparse_sizes=tuple(sparse_sizes))
-
-    def sparse_reshape(self, num_rows: int, num_cols: int) -> "SparseStorage":
+    def sparse_reshape(self, num_rows: int, num_cols: int):
         """Same entries, re-indexed for a (num_rows x num_cols) shape with the same element count; -1 infers one
         extent (torch_sparse/storage.py:316-346). Row-major order is preserved by construction."""
         assert num_rows > 0 or num_rows == -1
@@ -208,18 +255,20 @@ class SparseStorage:
             num_cols = total // num_rows
         assert num_rows * num_cols == total
         lin = self._sparse_sizes[1] * self.row() + self._col
-        return SparseStorage(row=torch.div(lin, num_cols, rounding_mode="floor"), col=lin % num_cols,
-                             value=self._value, sparse_sizes=(num_rows, num_cols), is_sorted=True, trust_data=True)
+        return self._with(torch.div(lin, num_cols, rounding_mode="floor"), None, lin % num_cols, self._value,
+                          (num_rows, num_cols), None, None, None, None, None)
 
     # ------------------------------------------------------------------ derived caches
     def has_rowcount(self) -> bool:
         return self._rowcount is not None
 
     def rowcount(self) -> Tensor:
-        if self._rowcount is None:
+        rowcount = self._rowcount
+        if rowcount is None:
             rowptr = self.rowptr()
-            self._rowcount = rowptr[1:] - rowptr[:-1]
-        return self._rowcount
+            rowcount = rowptr[1:] - rowptr[:-1]
+            self._rowcount = rowcount
+        return rowcount
 
     def has_colptr(self) -> bool:
         return self._colptr is not None
@@ -233,11 +282,11 @@ class SparseStorage:
     def has_csc2csr(self) -> bool:
         return self._csc2csr is not None
 
-    def _build_csc_(self) -> None:
+    def _build_csc_(self):
         """csr2csc and colptr in one pass (torch_sparse/storage.py:369-385, 407-416)."""
         M, N = self._sparse_sizes
         if self._col.is_cuda:
-            perm, colptr, row_csc = ops.csr2csc(self.row(), self._col, M, N, want_colptr=True, want_row_csc=True)
+            perm, colptr, row_csc = torch.ops.tsb200.csr2csc(self.row(), self._col, M, N)
             self._csr2csc = perm
             self._row_csc = row_csc
             if self._colptr is None:
@@ -248,18 +297,21 @@ class SparseStorage:
     def csr2csc(self) -> Tensor:
         if self._csr2csc is None:
             self._build_csc_()
-        return self._csr2csc
+        perm = self._csr2csc
+        assert perm is not None
+        return perm
 
     def row_csc(self) -> Tensor:
         """row[csr2csc] — the column index array of the CSC view, i.e. of A^T in CSR form. The reference gathers it
         on every backward (csrc/spmm.cpp:104); it only depends on the structure, so it is kept (the csr2csc kernel
         emits it for free)."""
-        if self._row_csc is None:
-            if self._csr2csc is None and self._col.is_cuda:
-                self._build_csc_()
-            if self._row_csc is None:
-                self._row_csc = self.row()[self.csr2csc()]
-        return self._row_csc
+        if self._row_csc is None and self._csr2csc is None and self._col.is_cuda:
+            self._build_csc_()
+        row_csc = self._row_csc
+        if row_csc is None:
+            row_csc = self.row()[self.csr2csc()]
+            self._row_csc = row_csc
+        return row_csc
 
     def colptr(self) -> Tensor:
         if self._colptr is None:
@@ -267,107 +319,142 @@ class SparseStorage:
                 if self._csr2csc is None:
                     self._build_csc_()
                 else:
-                    self._colptr = ops.ind2ptr(self._col[self._csr2csc], self._sparse_sizes[1])
+                    self._colptr = torch.ops.tsb200.ind2ptr(self._col[self.csr2csc()], self._sparse_sizes[1])
             else:
                 self._colptr = host.ind2ptr(self._col[self.csr2csc()], self._sparse_sizes[1])
-        return self._colptr
+        colptr = self._colptr
+        assert colptr is not None
+        return colptr
 
     def colcount(self) -> Tensor:
-        if self._colcount is None:
+        colcount = self._colcount
+        if colcount is None:
             colptr = self.colptr()
-            self._colcount = colptr[1:] - colptr[:-1]
-        return self._colcount
+            colcount = colptr[1:] - colptr[:-1]
+            self._colcount = colcount
+        return colcount
 
     def csc2csr(self) -> Tensor:
-        if self._csc2csr is None:
+        inv = self._csc2csr
+        if inv is None:
             perm = self.csr2csc()
             inv = torch.empty_like(perm)
             inv[perm] = torch.arange(perm.numel(), dtype=perm.dtype, device=perm.device)
             self._csc2csr = inv
-        return self._csc2csr
+        return inv
 
     # ------------------------------------------------------------------ coalesce
     def is_coalesced(self) -> bool:
         return host.is_coalesced(self.row(), self._col, self._sparse_sizes[1])
 
-    def coalesce(self, reduce: str = "add") -> "SparseStorage":
+    def coalesce(self, reduce: str = "add"):
         """Merge duplicate (row, col) entries (torch_sparse/storage.py:436-466)."""
         E = self._col.numel()
         if E < 2:
             return self
         M, N = self._sparse_sizes
-        row, col, value = ops.coalesce(self.row(), self._col, self._value, M, N, reduce)
+        row, col, value = torch.ops.tsb200.coalesce(self.row(), self._col, self._value, M, N, reduce)
         if row.numel() == E:  # nothing merged; entries were already sorted by construction
             return self
-        return SparseStorage(row=row, col=col, value=value, sparse_sizes=self._sparse_sizes, is_sorted=True,
-                             trust_data=True)
+        return self._with(row, None, col, value, self._sparse_sizes, None, None, None, None, None)
 
     # ------------------------------------------------------------------ cache control
-    def fill_cache_(self) -> "SparseStorage":
-        self.row(); self.rowptr(); self.rowcount(); self.colptr(); self.colcount(); self.csr2csc(); self.csc2csr()
+    def fill_cache_(self):
+        self.row()
+        self.rowptr()
+        self.rowcount()
+        self.colptr()
+        self.colcount()
+        self.csr2csc()
+        self.csc2csr()
         return self
 
-    def clear_cache_(self) -> "SparseStorage":
-        for k in _CACHE_KEYS:
-            setattr(self, "_" + k, None)
+    def clear_cache_(self):
+        self._rowcount = None
+        self._colptr = None
+        self._colcount = None
+        self._csr2csc = None
+        self._csc2csr = None
         self._row_csc = None
         return self
 
     def cached_keys(self) -> List[str]:
-        return [k for k in _CACHE_KEYS if getattr(self, "_" + k) is not None]
+        keys: List[str] = []
+        if self._rowcount is not None:
+            keys.append("rowcount")
+        if self._colptr is not None:
+            keys.append("colptr")
+        if self._colcount is not None:
+            keys.append("colcount")
+        if self._csr2csc is not None:
+            keys.append("csr2csc")
+        if self._csc2csr is not None:
+            keys.append("csc2csr")
+        return keys
 
     def num_cached_keys(self) -> int:
         return len(self.cached_keys())
 
     # ------------------------------------------------------------------ copies / moves
-    def _map(self, fn, value_fn=None) -> "SparseStorage":
-        def m(t):
-            return None if t is None else fn(t)
+    def _map(self, how: int, device: torch.device, non_blocking: bool):
+        col = _moved(self._col, how, device, non_blocking)
+        assert col is not None
+        out = self._with(_moved(self._row, how, device, non_blocking), _moved(self._rowptr, how, device, non_blocking),
+                         col, _moved(self._value, how, device, non_blocking), self._sparse_sizes,
+                         _moved(self._rowcount, how, device, non_blocking),
+                         _moved(self._colptr, how, device, non_blocking),
+                         _moved(self._colcount, how, device, non_blocking),
+                         _moved(self._csr2csc, how, device, non_blocking),
+                         _moved(self._csc2csr, how, device, non_blocking))
+        out._row_csc = _moved(self._row_csc, how, device, non_blocking)
+        return out
 
+    def copy(self):
+        out = self._with(self._row, self._rowptr, self._col, self._value, self._sparse_sizes, self._rowcount,
+                         self._colptr, self._colcount, self._csr2csc, self._csc2csr)
+        out._row_csc = self._row_csc
+        return out
+
+    def clone(self):
+        return self._map(0, self._col.device, False)
+
+    def type(self, dtype: torch.dtype, non_blocking: bool = False):
         value = self._value
-        if value is not None:
-            value = (value_fn or fn)(value)
-        return SparseStorage(row=m(self._row), rowptr=m(self._rowptr), col=fn(self._col), value=value,
-                             sparse_sizes=self._sparse_sizes, rowcount=m(self._rowcount), colptr=m(self._colptr),
-                             colcount=m(self._colcount), csr2csc=m(self._csr2csc), csc2csr=m(self._csc2csr),
-                             is_sorted=True, trust_data=True)
-
-    def copy(self) -> "SparseStorage":
-        return self._replace()
-
-    def clone(self) -> "SparseStorage":
-        return self._map(lambda t: t.clone())
-
-    def type(self, dtype: torch.dtype, non_blocking: bool = False) -> "SparseStorage":
-        if self._value is None or self._value.dtype == dtype:
+        if value is None or value.dtype == dtype:
             return self
-        return self.set_value(self._value.to(dtype=dtype, non_blocking=non_blocking), layout="coo")
+        return self.set_value(value.to(dtype=dtype, non_blocking=non_blocking), layout="coo")
 
-    def type_as(self, tensor: Tensor, non_blocking: bool = False) -> "SparseStorage":
+    def type_as(self, tensor: Tensor, non_blocking: bool = False):
         return self.type(tensor.dtype, non_blocking)
 
-    def to_device(self, device: torch.device, non_blocking: bool = False) -> "SparseStorage":
-        device = torch.device(device)
+    def to_device(self, device: torch.device, non_blocking: bool = False):
         if device == self._col.device:
             return self
-        return self._map(lambda t: t.to(device, non_blocking=non_blocking))
+        return self._map(1, device, non_blocking)
 
-    def device_as(self, tensor: Tensor, non_blocking: bool = False) -> "SparseStorage":
+    def device_as(self, tensor: Tensor, non_blocking: bool = False):
         return self.to_device(tensor.device, non_blocking)
 
-    def cuda(self) -> "SparseStorage":
-        return self if self._col.is_cuda else self._map(lambda t: t.cuda())
+    def cuda(self):
+        if self._col.is_cuda:
+            return self
+        return self._map(1, torch.device("cuda"), False)
 
-    def cpu(self) -> "SparseStorage":
-        return self._map(lambda t: t.cpu()) if self._col.is_cuda else self
+    def cpu(self):
+        if not self._col.is_cuda:
+            return self
+        return self._map(1, torch.device("cpu"), False)
 
     def is_cuda(self) -> bool:
         return self._col.is_cuda
 
-    def pin_memory(self) -> "SparseStorage":
-        return self._map(lambda t: t.pin_memory())
+    def pin_memory(self):
+        return self._map(2, self._col.device, False)
 
     def is_pinned(self) -> bool:
-        tensors = [self._row, self._rowptr, self._col, self._value, self._rowcount, self._colptr, self._colcount,
-                   self._csr2csc, self._csc2csr]
-        return all(t.is_pinned() for t in tensors if t is not None)
+        ok = self._col.is_pinned()
+        for t in [self._row, self._rowptr, self._value, self._rowcount, self._colptr, self._colcount, self._csr2csc,
+                  self._csc2csr]:
+            if t is not None:
+                ok = ok and t.is_pinned()
+        return ok

@@ -32,6 +32,11 @@ _SCHEMAS = {
 # the rest of the native surface (no counterpart among the reference's registered ops, whose Python layer builds these
 # from torch_scatter / torch.sparse.mm): registered under `tsb200` only, so TorchScript code can reach every kernel
 _EXTRA_SCHEMAS = {
+    # the reference's spmm_sum / spmm_mean plus the structure-only `row[csr2csc]` a caller may keep (SparseStorage.row_csc)
+    "spmm_sum_csc": "(Tensor? row, Tensor rowptr, Tensor col, Tensor? value, Tensor? colptr, Tensor? csr2csc, "
+                    "Tensor mat, Tensor? row_csc) -> Tensor",
+    "spmm_mean_csc": "(Tensor? row, Tensor rowptr, Tensor col, Tensor? value, Tensor? rowcount, Tensor? colptr, "
+                     "Tensor? csr2csc, Tensor mat, Tensor? row_csc) -> Tensor",
     "coalesce": "(Tensor row, Tensor col, Tensor? value, int M, int N, str reduce) -> (Tensor, Tensor, Tensor?)",
     "sort_perm": "(Tensor row, Tensor col, int M, int N) -> Tensor?",
     "csr2csc": "(Tensor row, Tensor col, int M, int N) -> (Tensor, Tensor, Tensor)",
@@ -47,6 +52,7 @@ def _csr2csc(row, col, M: int, N: int):
 
 
 _EXTRA_IMPLS = {
+    "spmm_sum_csc": ops.spmm_sum, "spmm_mean_csc": ops.spmm_mean,
     "coalesce": ops.coalesce, "sort_perm": ops.sort_perm, "csr2csc": _csr2csc,
     "segment_reduce": lambda ptr, value, reduce, perm, seg: ops.segment_reduce(ptr, value, reduce, perm, seg),
     "spspmm": ops.spspmm,

@@ -2,7 +2,7 @@
   * tensors created without an explicit device land on cuda:0 (several reference tests build CPU tensors
     unconditionally; the package under test is GPU-only),
   * every test starts from the same RNG seed (the reference's tests draw unseeded randn inputs),
-  * tests listed in tests/ref_suite_xfail.json are marked xfail(strict) with the recorded reason,
+  * tests listed in tests/ref_suite_xfail.json (currently none) are marked xfail with the recorded reason,
   * the outcome of every test id is written to $TSB200_REF_REPORT as JSON."""
 import fnmatch
 import json
@@ -25,7 +25,7 @@ def pytest_collection_modifyitems(config, items):
         nid = item.nodeid.split("/")[-1]
         for pat, reason in _XFAIL.items():
             if fnmatch.fnmatch(nid, pat):
-                item.add_marker(pytest.mark.xfail(reason=reason, strict=True))
+                item.add_marker(pytest.mark.xfail(reason=reason, strict=False))
                 break
 
 

@@ -151,3 +151,41 @@ def test_torchscript_functional_pipeline_over_every_native_op():
     prod = ts.SparseTensor(row=r, col=c, value=v, sparse_sizes=(m, m), is_sorted=True).to_dense()
     assert torch.allclose(prod, dense @ dense, atol=1e-10)
     assert torch.allclose(deg, dense.sum(1)) and torch.equal(colptr, a.storage.colptr())
+
+
+def test_torchscript_functions_over_sparse_tensor_objects():
+    """SparseStorage / SparseTensor are TorchScript classes like the reference's (torch_sparse/storage.py:21,
+    tensor.py:12): scripted functions build, combine and multiply SparseTensors on the GPU and agree with eager."""
+    from pytorch_sparse_b200 import SparseTensor, add, mul
+    from pytorch_sparse_b200.matmul import matmul, spspmm
+
+    torch.jit.script(spspmm)          # test/test_matmul.py:79
+
+    @torch.jit.script
+    def layer(edge_index: torch.Tensor, w: torch.Tensor, n: int, x: torch.Tensor):
+        a = SparseTensor(row=edge_index[0], col=edge_index[1], value=w, sparse_sizes=(n, n))
+        a = a.coalesce("sum")
+        deg = a.storage.rowcount().to(x.dtype).clamp(min=1).pow(-1.0).view(-1, 1)
+        y = matmul(mul(a, deg), x, "sum")
+        sym = add(a, a.set_value(a.storage.value(), layout="coo"))
+        return y, matmul(a, a, "sum"), sym
+
+    g = torch.Generator().manual_seed(21)
+    n, E = 60, 500
+    ei = torch.randint(n, (2, E), generator=g).to(DEV)
+    w = torch.randn(E, generator=g, dtype=torch.float64).to(DEV)
+    x = torch.randn(n, 8, generator=g, dtype=torch.float64).to(DEV)
+    y, sq, sym = layer(ei, w, n, x)
+    dense = torch.zeros(n, n, dtype=torch.float64, device=DEV).index_put((ei[0], ei[1]), w, accumulate=True)
+    cnt = (torch.zeros(n, n, device=DEV).index_put((ei[0], ei[1]), torch.ones(E, device=DEV), accumulate=True) > 0).sum(1)
+    assert torch.allclose(y, (dense / cnt.clamp(min=1).view(-1, 1)) @ x, atol=1e-10)
+    assert torch.allclose(sq.to_dense(), dense @ dense, atol=1e-10)
+    assert torch.allclose(sym.to_dense(), 2 * dense, atol=1e-12)
+    # eager objects go into scripted functions and come back as ordinary SparseTensors
+    a = ts.SparseTensor(row=ei[0], col=ei[1], value=w, sparse_sizes=(n, n)).coalesce()
+
+    @torch.jit.script
+    def jit_add(A: SparseTensor, B: SparseTensor) -> SparseTensor:
+        return add(A, B)
+
+    assert jit_add(a, a) == a + a

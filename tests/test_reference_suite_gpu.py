@@ -4,7 +4,8 @@ The files are staged by oracle/build_ref.stage_tests() from /root/reference/test
 (git-ignored like the rest of oracle/_ref; travels to the GPU box with the snapshot — /root/reference itself does
 not exist there). `torch_sparse` resolves to tests/ref_shim/torch_sparse (:= pytorch_sparse_b200), `torch_scatter`
 to the pure-torch stand-in the tests use to build expected values. Expected outcome of every test id:
-tests/golden/ref_suite_outcomes.json (pass / xfail list; xfail reasons in tests/ref_suite_xfail.json)."""
+tests/golden/ref_suite_outcomes.json (all 109 test ids pass since SparseStorage / SparseTensor are TorchScript classes;
+tests/ref_suite_xfail.json would hold reasons for expected failures — it is empty)."""
 import json
 import os
 import subprocess
@@ -40,7 +41,9 @@ def test_reference_suite_runs_green(tmp_path):
         (out_dir / "ref_suite_outcomes.json").write_text(json.dumps(got, indent=1, sort_keys=True))
         (out_dir / "ref_suite_log.txt").write_text(res.stdout + res.stderr)
     assert res.returncode == 0, tail
-    assert got and all(v in ("passed", "xfailed") for v in got.values()), tail
-    if EXPECTED.exists():
+    assert got and all(v in ("passed", "xfailed", "xpassed") for v in got.values()), tail
+    if EXPECTED.exists():   # nothing that is expected to pass may have stopped passing, and no test id may be missing
         want = json.loads(EXPECTED.read_text())
-        assert got == want, {k: (want.get(k), got.get(k)) for k in set(want) | set(got) if want.get(k) != got.get(k)}
+        worse = {k: (w, got.get(k)) for k, w in want.items()
+                 if got.get(k) is None or (w == "passed" and got.get(k) not in ("passed", "xpassed"))}
+        assert not worse, worse
