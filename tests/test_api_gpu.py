@@ -4,6 +4,8 @@ import pytest
 import torch
 
 import pytorch_sparse_b200 as ts
+from pytorch_sparse_b200 import SparseTensor, add, mul   # module level: TorchScript resolves annotations from globals
+from pytorch_sparse_b200.matmul import matmul, spspmm
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -156,9 +158,6 @@ def test_torchscript_functional_pipeline_over_every_native_op():
 def test_torchscript_functions_over_sparse_tensor_objects():
     """SparseStorage / SparseTensor are TorchScript classes like the reference's (torch_sparse/storage.py:21,
     tensor.py:12): scripted functions build, combine and multiply SparseTensors on the GPU and agree with eager."""
-    from pytorch_sparse_b200 import SparseTensor, add, mul
-    from pytorch_sparse_b200.matmul import matmul, spspmm
-
     torch.jit.script(spspmm)          # test/test_matmul.py:79
 
     @torch.jit.script
