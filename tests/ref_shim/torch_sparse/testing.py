@@ -1,13 +1,16 @@
-"""Stand-in for torch_sparse/testing.py:1-21 with the device list reduced to the GPU (this package has no CPU path)."""
-from typing import Any
-
+"""What the reference's test files import from `torch_sparse.testing` (torch_sparse/testing.py:1-21), for the
+reference-suite run against this package: the parameter lists, with the device list reduced to the GPU (this package has
+no CPU path), and the small tensor factory."""
 import torch
 
-reductions = ['sum', 'add', 'mean', 'min', 'max']
-dtypes = [torch.half, torch.float, torch.double, torch.int, torch.long, torch.bfloat16]
-grad_dtypes = [torch.half, torch.float, torch.double, torch.bfloat16]
-devices = [torch.device('cuda:0')]
+devices = [torch.device("cuda", 0)]
+reductions = "sum add mean min max".split()
+grad_dtypes = [getattr(torch, name) for name in ("half", "float", "double", "bfloat16")]
+dtypes = grad_dtypes[:3] + [torch.int, torch.long] + grad_dtypes[3:]
 
 
-def tensor(x: Any, dtype: torch.dtype, device: torch.device):
-    return None if x is None else torch.tensor(x, dtype=dtype, device=device)
+def tensor(x, dtype, device):
+    """`x` as a tensor of `dtype` on `device`; None stays None."""
+    if x is None:
+        return None
+    return torch.tensor(x, dtype=dtype, device=device)
