@@ -282,3 +282,50 @@ def test_cuda_version_op_matches_reference_encoding():
     # CUDA_VERSION encoding (csrc/version.cpp:27-41); the reference's import check (torch_sparse/__init__.py:23-37)
     # derives major from the first two digits and must agree with torch's CUDA major
     assert v >= 12000 and int(str(v)[0:2]) == int(torch.version.cuda.split(".")[0])
+
+
+@torch.jit.script
+def _scripted_views(row: torch.Tensor, col: torch.Tensor, value: torch.Tensor, M: int, N: int):
+    st = ts.SparseStorage(row=row, col=col, value=value, sparse_sizes=(M, N))
+    st.fill_cache_()
+    value = st.value()
+    assert value is not None
+    return (st.row(), st.col(), value, st.rowptr(), st.rowcount(), st.colptr(), st.colcount(), st.csr2csc(),
+            st.csc2csr(), st.num_cached_keys())
+
+
+def test_scripted_storage_matches_reference_views():
+    """SparseStorage is a TorchScript class (torch_sparse/storage.py:21): built and queried from COMPILED code on CPU
+    tensors (index bookkeeping only), it reproduces the unmodified reference's nine views bit for bit
+    (tests/golden/storage_views.pt)."""
+    d = torch.load(Path(__file__).resolve().parent / "golden" / "storage_views.pt", weights_only=False)
+    i, o = d["in"], d["out"]
+    got = _scripted_views(i["row"], i["col"], i["value"], i["M"], i["N"])
+    names = ("row", "col", "value", "rowptr", "rowcount", "colptr", "colcount", "csr2csc", "csc2csr")
+    for name, t in zip(names, got[:9]):
+        assert torch.equal(t, o[name]), name
+    assert got[9] == 5
+
+
+def test_scripted_sparse_tensor_api_on_cpu():
+    """SparseTensor as a TorchScript class: scripted code builds tensors, reshapes, resizes, converts and compares —
+    everything that is index bookkeeping runs compiled on CPU tensors."""
+    from pytorch_sparse_b200 import SparseTensor
+
+    @torch.jit.script
+    def f(dense: torch.Tensor):
+        idx = dense.nonzero().t()     # (class-level constructors such as from_dense are eager-only conveniences)
+        a = SparseTensor(row=idx[0], col=idx[1], value=dense[idx[0], idx[1]], sparse_sizes=(dense.size(0), dense.size(1)))
+        b = a.set_value(a.storage.value(), layout="coo").sparse_resize((dense.size(0) + 2, dense.size(1)))
+        c = a.sparse_reshape(dense.size(1), dense.size(0))
+        return a.to_dense(), b.sizes(), b.storage.rowptr(), c.to_dense(), a.is_symmetric(), a.density(), a.nnz()
+
+    g = torch.Generator().manual_seed(4)
+    dense = torch.randn(6, 4, generator=g, dtype=torch.float64) * (torch.rand(6, 4, generator=g) < 0.5)
+    back, sizes, rowptr, reshaped, sym, density, nnz = f(dense)
+    assert torch.equal(back, dense) and sizes == [8, 4] and rowptr.numel() == 9 and int(rowptr[-1]) == nnz
+    assert torch.equal(reshaped, dense.reshape(4, 6)) and sym is False
+    assert abs(density - (dense != 0).sum().item() / 24) < 1e-12
+    # eager and scripted objects are the same Python class
+    a = SparseTensor.from_dense(dense)
+    assert isinstance(a, SparseTensor) and a == SparseTensor.from_dense(back)
