@@ -93,6 +93,29 @@ TSB200_API int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
                    int64_t E, int dtype, int reduce, void* workspace, size_t workspace_bytes,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Planned SpMM (no counterpart in the reference; the analogue of the structure caches it keeps, csr2csc / colptr).
+ *   The only data-dependent control decision of the forward kernel — which rows are too long (or overflow their
+ *   32-row group's nnz budget) and are therefore cut into <= 256-nnz segments — depends on rowptr alone.
+ *   tsb200_spmm_plan computes it once per matrix: a row mask, the segment list and the multi-segment rows, into
+ *   `plan` (tsb200_spmm_plan_bytes(M, E) bytes, 256 B aligned), and returns the three counts
+ *   counts_host[0..2] = {segments, multi-segment rows, partial slots} (synchronises `stream` once).
+ *   tsb200_spmm_fw_planned then runs ANY product with that matrix (same semantics as tsb200_spmm_fw, B = 1,
+ *   F32 / F16 / BF16 with K * sizeof(dtype) % 16 == 0) as one memset + ONE kernel: the warps process the row items
+ *   and then drain the plan's segment list themselves; a multi-segment row is combined by the warp that finishes its
+ *   last segment. (For K * sizeof(dtype) <= 128 B the segment / combine kernels are still separate launches, issued
+ *   only when the plan holds segments.) workspace: tsb200_spmm_fw_planned_workspace_bytes(K, n_long, n_slot, reduce).
+ * ------------------------------------------------------------------------------------------ */
+TSB200_API size_t tsb200_spmm_plan_bytes(int64_t M, int64_t E);
+TSB200_API int tsb200_spmm_plan(const int64_t* rowptr, int64_t M, int64_t E, void* plan, size_t plan_bytes,
+                                int64_t* counts_host, void* stream);
+TSB200_API size_t tsb200_spmm_fw_planned_workspace_bytes(int64_t K, int64_t n_long, int64_t n_slot, int reduce);
+TSB200_API int tsb200_spmm_fw_planned(const int64_t* rowptr, const int64_t* col, const void* value, const void* mat,
+                                      void* out, int64_t* arg_out, int64_t M, int64_t N, int64_t K, int64_t E,
+                                      int dtype, int reduce, const void* plan, size_t plan_bytes, int64_t n_seg,
+                                      int64_t n_long, int64_t n_slot, void* workspace, size_t workspace_bytes,
+                                      void* stream);
+
 /* One COLUMN BLOCK of a SUM SpMM (multi-GPU pipelining: the dense operand arrives block by block over NVLink and
  * block p of A's columns is multiplied as soon as block p of `mat` has landed; no counterpart in the reference, which
  * has no collectives — the partitioner semantics are torch_sparse/narrow.py:15-42). (rowptr, col, value) hold only the

@@ -24,6 +24,12 @@ SIGNATURES = {
     "tsb200_spmm_fw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
                                c_void_p, c_size_t, c_void_p]),
+    "tsb200_spmm_plan_bytes": (c_size_t, [c_int64, c_int64]),
+    "tsb200_spmm_plan": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tsb200_spmm_fw_planned_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int]),
+    "tsb200_spmm_fw_planned": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_size_t,
+                                       c_int64, c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "tsb200_spmm_fw_acc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                    c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "tsb200_spmm_value_bw_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64, c_int]),

@@ -47,6 +47,13 @@ struct SpmmParams {
   // L2 residency of the dense operand: 0 = evict_last on every gather; otherwise the first pin_bytes of `mat`
   // (total mat_bytes < 4 GB) are evict_last and the rest evict_first (make_policy_range)
   uint32_t pin_bytes, mat_bytes;
+  // planned mode (tsb200_spmm_plan, B == 1): which rows go through the segment list is known up front — bit r of
+  // plan_mask[r / 32] — the list itself (segs / longs above) lives in the plan, its sizes are host-known, and the
+  // main kernel drains it itself once the row items are gone (no segment / combine launches)
+  const uint32_t* plan_mask;
+  const uint32_t* seg_lr;   // long-row index of every segment (for the last-finisher combine)
+  uint32_t* long_done;      // per call, zeroed: finished segments per long row
+  int64_t n_seg, n_long;
   // workspace
   unsigned int* counters;  // [0] item counter, [1] #segments, [2] #long rows, [3] #partial slots
   Segment* segs;

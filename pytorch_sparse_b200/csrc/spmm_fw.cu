@@ -372,7 +372,34 @@ template <typename T, int RED, int LPR, int CH, int U> struct EngineFor {
                                          RowEngine<T, RED, LPR, CH, U>>::type;
 };
 
-template <typename T, int RED, int LPR, int CH, int U, int MINB, bool ACC = false>
+// combine the partials of one multi-segment row, in segment order, by ONE WARP (planned mode: the warp that finished
+// the row's last segment); the partials were written by other SMs -> read them past L1
+template <typename T, int RED>
+__device__ __forceinline__ void combine_row_warp(const SpmmParams& p, const LongRow& L, int lane, int kcols) {
+  constexpr bool ARG = (RED == R_MIN || RED == R_MAX);
+  const int nseg = (int)(L.nseg_count >> 40);
+  const int64_t count = L.nseg_count & (((int64_t)1 << 40) - 1);
+  for (int k = lane; k < kcols; k += 32) {
+    const int64_t kk = p.k0 + k;
+    if (kk >= p.K) break;
+    float a = __ldcg((const float*)p.part_val + L.first_slot * p.K + kk);
+    int64_t ar = ARG ? __ldcg(p.part_arg + L.first_slot * p.K + kk) : 0;
+    for (int sgi = 1; sgi < nseg; sgi++) {
+      const float v = __ldcg((const float*)p.part_val + (L.first_slot + sgi) * p.K + kk);
+      if (RED == R_SUM) a += v;
+      else {
+        const int64_t va = __ldcg(p.part_arg + (L.first_slot + sgi) * p.K + kk);
+        const bool better = (RED == R_MIN) ? (v < a) : (v > a);
+        if (better || (v == a && va < ar)) { a = v; ar = va; }
+      }
+    }
+    if (RED == R_SUM && p.mean) a = a / (float)(count > 0 ? count : 1);
+    ((T*)p.out)[L.row_b * p.K + kk] = Traits<T>::from_acc(a);
+    if (ARG) p.arg_out[L.row_b * p.K + kk] = ar;
+  }
+}
+
+template <typename T, int RED, int LPR, int CH, int U, int MINB, bool ACC = false, bool PLAN = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_vec_kernel(const SpmmParams p) {
   using Eng = typename EngineFor<T, RED, LPR, CH, U>::type;
@@ -425,40 +452,46 @@ spmm_vec_kernel(const SpmmParams p) {
     const int s_rel = (int)(rp0 - base), e_rel = (int)(rp1 - base);
     const int deg = e_rel - s_rel;
 
-    // nnz budget: prefix sum of the degrees of the non-long rows
-    const bool is_long = deg > kLongT;
-    int cum = is_long ? 0 : deg;
+    unsigned defer_mask;
+    if constexpr (PLAN) {  // which rows are in the segment list was decided when the plan was built
+      const uint32_t w = __ldg(p.plan_mask + (r0 >> 5));
+      defer_mask = (w >> (r0 & 31)) & (nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+    } else {
+      // nnz budget: prefix sum of the degrees of the non-long rows
+      const bool is_long = deg > kLongT;
+      int cum = is_long ? 0 : deg;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, cum, off);
-      if (lane >= off) cum += t;
-    }
-    const bool defer = (deg > 0) && (is_long || cum > kItemCap);
-    const unsigned defer_mask = __ballot_sync(0xffffffffu, defer);
-
-    if (defer) {  // rare: push this row's segments
-      const int nseg = (deg + kSeg - 1) / kSeg;
-      const unsigned seg0 = atomicAdd(&p.counters[1], (unsigned)nseg);
-      int64_t slot0 = -1;
-      if (nseg > 1) {
-        slot0 = atomicAdd(&p.counters[3], (unsigned)nseg);
-        const unsigned lr = atomicAdd(&p.counters[2], 1u);
-        if ((int64_t)lr < p.long_cap) {
-          LongRow L;
-          L.row_b = b * p.M + r0 + lane;
-          L.first_slot = slot0;
-          L.nseg_count = ((int64_t)nseg << 40) | (int64_t)deg;
-          p.longs[lr] = L;
-        }
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, cum, off);
+        if (lane >= off) cum += t;
       }
-      for (int sgi = 0; sgi < nseg; sgi++) {
-        if ((int64_t)seg0 + sgi < p.seg_cap) {
-          Segment S;
-          S.row_b = b * p.M + r0 + lane;
-          S.start = rp0 + (int64_t)sgi * kSeg;
-          S.end = min(rp1, S.start + kSeg);
-          S.slot = slot0 < 0 ? -1 : slot0 + sgi;
-          p.segs[seg0 + sgi] = S;
+      const bool defer = (deg > 0) && (is_long || cum > kItemCap);
+      defer_mask = __ballot_sync(0xffffffffu, defer);
+
+      if (defer) {  // rare: push this row's segments
+        const int nseg = (deg + kSeg - 1) / kSeg;
+        const unsigned seg0 = atomicAdd(&p.counters[1], (unsigned)nseg);
+        int64_t slot0 = -1;
+        if (nseg > 1) {
+          slot0 = atomicAdd(&p.counters[3], (unsigned)nseg);
+          const unsigned lr = atomicAdd(&p.counters[2], 1u);
+          if ((int64_t)lr < p.long_cap) {
+            LongRow L;
+            L.row_b = b * p.M + r0 + lane;
+            L.first_slot = slot0;
+            L.nseg_count = ((int64_t)nseg << 40) | (int64_t)deg;
+            p.longs[lr] = L;
+          }
+        }
+        for (int sgi = 0; sgi < nseg; sgi++) {
+          if ((int64_t)seg0 + sgi < p.seg_cap) {
+            Segment S;
+            S.row_b = b * p.M + r0 + lane;
+            S.start = rp0 + (int64_t)sgi * kSeg;
+            S.end = min(rp1, S.start + kSeg);
+            S.slot = slot0 < 0 ? -1 : slot0 + sgi;
+            p.segs[seg0 + sgi] = S;
+          }
         }
       }
     }
@@ -484,6 +517,61 @@ spmm_vec_kernel(const SpmmParams p) {
     }
     item = __shfl_sync(0xffffffffu, next_item, 0);
   }
+
+  if constexpr (PLAN) {
+    // Planned mode: the row items are gone — this warp now takes segments of the long / over-budget rows from the
+    // plan's list (all of them exist already: a ticket counter is the whole protocol). A multi-segment row is
+    // combined by whichever warp finishes its last segment (counter per long row + fences, no waiting).
+    constexpr int kcols = LPR * CH * VEC;
+    while (true) {
+      unsigned int sidx = 0;
+      if (lane == 0) sidx = atomicAdd(&p.counters[5], 1u);
+      sidx = __shfl_sync(0xffffffffu, sidx, 0);
+      if ((int64_t)sidx >= p.n_seg) break;
+      const Segment S = p.segs[sidx];
+      const int64_t row = S.row_b;  // B == 1
+      const int64_t base = S.start & ~(int64_t)31;
+      ring.reset(base, S.end);
+      const char* matb = (const char*)p.mat + lane_off;
+      asm volatile("" : "+l"(matb));
+      Eng eng;
+      eng.init();
+      eng.accumulate(ring, (int)(S.start - base), (int)(S.end - base), matb, row_bytes, col_ok, lane, g, pol);
+      eng.reduce_groups();
+      if (S.slot < 0) {
+        if (g == 0)
+          eng.store_row((T*)p.out + row * p.K + p.k0, p.arg_out ? p.arg_out + row * p.K + p.k0 : nullptr,
+                        S.end - S.start, p.E, col_ok, li, p.mean != 0);
+      } else {
+        if (g == 0) {
+          float* pv = (float*)p.part_val + S.slot * p.K + p.k0;
+          int64_t* pa = Eng::ARG ? p.part_arg + S.slot * p.K + p.k0 : nullptr;
+#pragma unroll
+          for (int ch = 0; ch < CH; ch++) {
+            if (!col_ok[ch]) continue;
+            const int koff = (ch * LPR + li) * VEC;
+#pragma unroll
+            for (int i = 0; i < VEC; i++) {
+              pv[koff + i] = eng.acc_float(ch * VEC + i);
+              if (Eng::ARG) pa[koff + i] = eng.arg[ch * VEC + i] == 0x7fffffff ? p.E : (int64_t)eng.arg[ch * VEC + i];
+            }
+          }
+        }
+        __syncwarp();
+        __threadfence();  // this segment's partial is visible before its completion is counted
+        const uint32_t lr = __ldg(p.seg_lr + sidx);
+        unsigned int finished = 0;
+        if (lane == 0) finished = atomicAdd(&p.long_done[lr], 1u);
+        finished = __shfl_sync(0xffffffffu, finished, 0);
+        const LongRow L = p.longs[lr];
+        if ((int)finished == (int)(L.nseg_count >> 40) - 1) {
+          __threadfence();
+          combine_row_warp<T, RED>(p, L, lane, kcols);
+        }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // ---- narrow dense rows (K*sizeof(T) <= 128 B): group-per-row SUM kernel ----------------------------
@@ -502,7 +590,7 @@ template <> __device__ __forceinline__ unsigned short load_vraw<__half>(const __
   return __ldg(reinterpret_cast<const unsigned short*>(p));
 }
 
-template <typename T, int RED, int LPR, int U, int MINB, bool ACC = false>
+template <typename T, int RED, int LPR, int U, int MINB, bool ACC = false, bool PLAN = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 spmm_gpr_kernel(const SpmmParams p) {
   using V = Vec<T>;
@@ -540,40 +628,47 @@ spmm_gpr_kernel(const SpmmParams p) {
     const int s_rel = (int)(rp0 - base), e_rel = (int)(rp1 - base);
     const int deg = e_rel - s_rel;
 
-    const bool is_long = deg > kLongT;
-    int cum = is_long ? 0 : deg;
+    unsigned defer_mask;
+    if constexpr (PLAN) {
+      const uint32_t w = __ldg(p.plan_mask + (r0 >> 5));
+      defer_mask = (w >> (r0 & 31)) & (nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u));
+    } else {
+      const bool is_long = deg > kLongT;
+      int cum = is_long ? 0 : deg;
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, cum, off);
-      if (lane >= off) cum += t;
-    }
-    const bool defer = (deg > 0) && (is_long || cum > kItemCap);
-    const unsigned defer_mask = __ballot_sync(0xffffffffu, defer);
-    if (defer) {
-      const int nseg = (deg + kSeg - 1) / kSeg;
-      const unsigned seg0 = atomicAdd(&p.counters[1], (unsigned)nseg);
-      int64_t slot0 = -1;
-      if (nseg > 1) {
-        slot0 = atomicAdd(&p.counters[3], (unsigned)nseg);
-        const unsigned lr = atomicAdd(&p.counters[2], 1u);
-        if ((int64_t)lr < p.long_cap) {
-          LongRow L;
-          L.row_b = b * p.M + r0 + lane;
-          L.first_slot = slot0;
-          L.nseg_count = ((int64_t)nseg << 40) | (int64_t)deg;
-          p.longs[lr] = L;
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, cum, off);
+        if (lane >= off) cum += t;
+      }
+      const bool defer = (deg > 0) && (is_long || cum > kItemCap);
+      defer_mask = __ballot_sync(0xffffffffu, defer);
+      if (defer) {
+        const int nseg = (deg + kSeg - 1) / kSeg;
+        const unsigned seg0 = atomicAdd(&p.counters[1], (unsigned)nseg);
+        int64_t slot0 = -1;
+        if (nseg > 1) {
+          slot0 = atomicAdd(&p.counters[3], (unsigned)nseg);
+          const unsigned lr = atomicAdd(&p.counters[2], 1u);
+          if ((int64_t)lr < p.long_cap) {
+            LongRow L;
+            L.row_b = b * p.M + r0 + lane;
+            L.first_slot = slot0;
+            L.nseg_count = ((int64_t)nseg << 40) | (int64_t)deg;
+            p.longs[lr] = L;
+          }
+        }
+        for (int sgi = 0; sgi < nseg; sgi++) {
+          if ((int64_t)seg0 + sgi < p.seg_cap) {
+            Segment S;
+            S.row_b = b * p.M + r0 + lane;
+            S.start = rp0 + (int64_t)sgi * kSeg;
+            S.end = min(rp1, S.start + kSeg);
+            S.slot = slot0 < 0 ? -1 : slot0 + sgi;
+            p.segs[seg0 + sgi] = S;
+          }
         }
       }
-      for (int sgi = 0; sgi < nseg; sgi++) {
-        if ((int64_t)seg0 + sgi < p.seg_cap) {
-          Segment S;
-          S.row_b = b * p.M + r0 + lane;
-          S.start = rp0 + (int64_t)sgi * kSeg;
-          S.end = min(rp1, S.start + kSeg);
-          S.slot = slot0 < 0 ? -1 : slot0 + sgi;
-          p.segs[seg0 + sgi] = S;
-        }
-      }
+    
     }
     __syncwarp();
 
@@ -677,7 +772,7 @@ spmm_seg_kernel(const SpmmParams p) {
   const uint32_t row_bytes = (uint32_t)(p.K * (int64_t)sizeof(T));
   const int64_t lane_off = ((int64_t)p.k0 + (int64_t)li * VEC) * (int64_t)sizeof(T);
 
-  const int64_t nseg = min((int64_t)p.counters[1], p.seg_cap);
+  const int64_t nseg = p.plan_mask ? p.n_seg : min((int64_t)p.counters[1], p.seg_cap);
   const int64_t wstride = (int64_t)gridDim.x * kWarpsPerCta;
   for (int64_t sidx = (int64_t)blockIdx.x * kWarpsPerCta + warp; sidx < nseg; sidx += wstride) {
     const Segment S = p.segs[sidx];
@@ -719,7 +814,7 @@ spmm_seg_kernel(const SpmmParams p) {
 template <typename T, int RED>
 __global__ void spmm_combine_kernel(const SpmmParams p, int kcols) {
   constexpr bool ARG = (RED == R_MIN || RED == R_MAX);
-  const int64_t nlong = min((int64_t)p.counters[2], p.long_cap);
+  const int64_t nlong = p.plan_mask ? p.n_long : min((int64_t)p.counters[2], p.long_cap);
   for (int64_t li = blockIdx.x; li < nlong; li += gridDim.x) {
     const LongRow L = p.longs[li];
     const int nseg = (int)(L.nseg_count >> 40);
@@ -818,18 +913,17 @@ static bool vec_eligible(int dtype, int64_t K, int64_t E, int64_t N, const void*
   return true;
 }
 
-template <typename T, int RED, bool ACC, int LPR, int CH, int U, int MINB = 1, bool GPR = false>
+template <typename T, int RED, bool ACC, int LPR, int CH, int U, int MINB = 1, bool GPR = false, bool PLAN = false>
 static int launch_vec(SpmmParams p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   constexpr int kcols = LPR * CH * VEC;
   void (*kmain)(const SpmmParams);
-  if constexpr (GPR) kmain = spmm_gpr_kernel<T, RED, LPR, U, MINB, ACC>;
-  else kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB, ACC>;
+  if constexpr (GPR) kmain = spmm_gpr_kernel<T, RED, LPR, U, MINB, ACC, PLAN>;
+  else kmain = spmm_vec_kernel<T, RED, LPR, CH, U, MINB, ACC, PLAN>;
   constexpr int USEG = (U > LPR) ? LPR : U;  // the row engine needs U * (32 / LPR) <= 32
   auto* kseg = spmm_seg_kernel<T, RED, LPR, CH, USEG, MINB, ACC>;
   static GridCache gc_main, gc_seg;  // per instantiation, per device
   const int grid_main = gc_main.get((const void*)kmain, kWarpsPerCta * 32);
-  const int grid_seg = gc_seg.get((const void*)kseg, kWarpsPerCta * 32);
   // small matrices: shrink the work item so that every resident warp gets rows
   int64_t want = p.M * p.B / ((int64_t)grid_main * kWarpsPerCta * 2);
   p.item_shift = 0;
@@ -837,14 +931,37 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
   const int64_t n_items = ((p.M + (1 << p.item_shift) - 1) >> p.item_shift) * p.B;
   for (int k0 = 0; k0 < p.K; k0 += kcols) {
     p.k0 = k0;
-    TSB_CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));
-    const int gm = (int)min((int64_t)grid_main, (n_items + kWarpsPerCta - 1) / kWarpsPerCta);
-    kmain<<<gm, kWarpsPerCta * 32, 0, st>>>(p);
-    TSB_LAUNCH_CHECK();
-    kseg<<<grid_seg, kWarpsPerCta * 32, 0, st>>>(p);
-    TSB_LAUNCH_CHECK();
-    spmm_combine_kernel<T, RED><<<num_sms() * 2, 128, 0, st>>>(p, kcols);
-    TSB_LAUNCH_CHECK();
+    if constexpr (PLAN) {
+      // one memset (ticket counters + the per-long-row completion counters behind them), ONE kernel: the row items,
+      // then the plan's segments, drained by the same warps. The group-per-row kernel has no index ring to drain
+      // with, so for narrow dense rows the segment / combine kernels are still launched — when the plan says there
+      // is something for them to do.
+      TSB_CUDA_TRY(cudaMemsetAsync(p.counters, 0, 256 + (size_t)p.n_long * 4, st));
+      int64_t work = (n_items + kWarpsPerCta - 1) / kWarpsPerCta;
+      if (!GPR) work = max(work, (p.n_seg + kWarpsPerCta - 1) / kWarpsPerCta);
+      const int gm = (int)max((int64_t)1, min((int64_t)grid_main, work));
+      kmain<<<gm, kWarpsPerCta * 32, 0, st>>>(p);
+      TSB_LAUNCH_CHECK();
+      if (GPR && p.n_seg > 0) {
+        const int grid_seg = gc_seg.get((const void*)kseg, kWarpsPerCta * 32);
+        kseg<<<grid_seg, kWarpsPerCta * 32, 0, st>>>(p);
+        TSB_LAUNCH_CHECK();
+        if (p.n_long > 0) {
+          spmm_combine_kernel<T, RED><<<num_sms() * 2, 128, 0, st>>>(p, kcols);
+          TSB_LAUNCH_CHECK();
+        }
+      }
+    } else {
+      const int grid_seg = gc_seg.get((const void*)kseg, kWarpsPerCta * 32);
+      TSB_CUDA_TRY(cudaMemsetAsync(p.counters, 0, 64, st));
+      const int gm = (int)min((int64_t)grid_main, (n_items + kWarpsPerCta - 1) / kWarpsPerCta);
+      kmain<<<gm, kWarpsPerCta * 32, 0, st>>>(p);
+      TSB_LAUNCH_CHECK();
+      kseg<<<grid_seg, kWarpsPerCta * 32, 0, st>>>(p);
+      TSB_LAUNCH_CHECK();
+      spmm_combine_kernel<T, RED><<<num_sms() * 2, 128, 0, st>>>(p, kcols);
+      TSB_LAUNCH_CHECK();
+    }
   }
   return 0;
 }
@@ -852,33 +969,124 @@ static int launch_vec(SpmmParams p, cudaStream_t st) {
 // (LPR, CH) follow from the width of a dense row; (U, MINB) = gathers in flight per lane and CTAs
 // per SM, tuned on B200 (profiles/r01_variant_sweep.txt): the kernel is HBM-latency bound, so
 // resident warps x gathers-in-flight wins; 40 warps/SM x 4 x 16 B per lane saturates HBM.
-template <typename T, int RED, bool ACC = false> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
+template <typename T, int RED, bool ACC = false, bool PLAN = false> static int dispatch_shape(const SpmmParams& p, cudaStream_t st) {
   constexpr int VEC = 16 / sizeof(T);
   const int64_t vecs = p.K / VEC;  // 16-byte vectors per dense row
   {  // narrow rows: group-per-row kernel (all reductions)
-    if (vecs <= 1) return launch_vec<T, RED, ACC, 1, 1, 4, 5, true>(p, st);
-    if (vecs <= 2) return launch_vec<T, RED, ACC, 2, 1, 4, 5, true>(p, st);
-    if (vecs <= 4) return launch_vec<T, RED, ACC, 4, 1, 4, 5, true>(p, st);
-    if (vecs <= 8) return launch_vec<T, RED, ACC, 8, 1, 4, 5, true>(p, st);
+    if (vecs <= 1) return launch_vec<T, RED, ACC, 1, 1, 4, 5, true, PLAN>(p, st);
+    if (vecs <= 2) return launch_vec<T, RED, ACC, 2, 1, 4, 5, true, PLAN>(p, st);
+    if (vecs <= 4) return launch_vec<T, RED, ACC, 4, 1, 4, 5, true, PLAN>(p, st);
+    if (vecs <= 8) return launch_vec<T, RED, ACC, 8, 1, 4, 5, true, PLAN>(p, st);
   }
-  if (vecs <= 1) return launch_vec<T, RED, ACC, 1, 1, 1, 6>(p, st);
-  if (vecs <= 4) return launch_vec<T, RED, ACC, 4, 1, 4, 5>(p, st);
-  if (vecs <= 8) return launch_vec<T, RED, ACC, 8, 1, 4, 5>(p, st);
-  if (vecs <= 16) return launch_vec<T, RED, ACC, 16, 1, 4, 5>(p, st);
-  if (vecs <= 32) return launch_vec<T, RED, ACC, 32, 1, 4, 5>(p, st);
-  if (vecs <= 64) return launch_vec<T, RED, ACC, 32, 2, 4, 3>(p, st);
-  return launch_vec<T, RED, ACC, 32, 4, 2, 3>(p, st);  // column-tiled beyond 128 vectors
+  if (vecs <= 1) return launch_vec<T, RED, ACC, 1, 1, 1, 6, false, PLAN>(p, st);
+  if (vecs <= 4) return launch_vec<T, RED, ACC, 4, 1, 4, 5, false, PLAN>(p, st);
+  if (vecs <= 8) return launch_vec<T, RED, ACC, 8, 1, 4, 5, false, PLAN>(p, st);
+  if (vecs <= 16) return launch_vec<T, RED, ACC, 16, 1, 4, 5, false, PLAN>(p, st);
+  if (vecs <= 32) return launch_vec<T, RED, ACC, 32, 1, 4, 5, false, PLAN>(p, st);
+  if (vecs <= 64) return launch_vec<T, RED, ACC, 32, 2, 4, 3, false, PLAN>(p, st);
+  return launch_vec<T, RED, ACC, 32, 4, 2, 3, false, PLAN>(p, st);  // column-tiled beyond 128 vectors
 }
 
-template <typename T> static int dispatch_red_vec(SpmmParams p, int reduce, cudaStream_t st) {
+template <typename T, bool PLAN = false> static int dispatch_red_vec(SpmmParams p, int reduce, cudaStream_t st) {
   p.mean = (reduce == TSB200_MEAN);
   switch (reduce) {
     case TSB200_SUM:
-    case TSB200_MEAN: return dispatch_shape<T, R_SUM>(p, st);
-    case TSB200_MIN: return dispatch_shape<T, R_MIN>(p, st);
-    case TSB200_MAX: return dispatch_shape<T, R_MAX>(p, st);
+    case TSB200_MEAN: return dispatch_shape<T, R_SUM, false, PLAN>(p, st);
+    case TSB200_MIN: return dispatch_shape<T, R_MIN, false, PLAN>(p, st);
+    case TSB200_MAX: return dispatch_shape<T, R_MAX, false, PLAN>(p, st);
   }
   return TSB200_ERR_INVALID_ARG;
+}
+
+// ---- plan: the segment list of a matrix, built once (tsb200_spmm_plan) -----------------------------------------
+// One warp per group of 32 rows, the same rule as the unplanned main kernels (rows longer than kLongT nnz, and rows
+// beyond the group's kItemCap-nnz budget, become <= kSeg-nnz segments); also leaves one mask word per group.
+__global__ void __launch_bounds__(256)
+spmm_plan_kernel(const int64_t* __restrict__ rowptr, int64_t M, uint32_t* __restrict__ mask, Segment* __restrict__ segs,
+                 uint32_t* __restrict__ seg_lr, LongRow* __restrict__ longs, unsigned int* __restrict__ counters,
+                 int64_t seg_cap, int64_t long_cap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ngroups = (M + 31) >> 5;
+  for (int64_t grp = wid; grp < ngroups; grp += nw) {
+    const int64_t r0 = grp << 5;
+    const int nrows = (int)min((int64_t)32, M - r0);
+    const int64_t rp0 = __ldg(rowptr + r0 + min(lane, nrows));
+    const int64_t rp1 = __ldg(rowptr + r0 + min(lane + 1, nrows));
+    const int64_t deg64 = rp1 - rp0;
+    const int deg = (int)min(deg64, (int64_t)0x3fffffff);
+    const bool is_long = deg > kLongT;
+    int cum = is_long ? 0 : deg;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, cum, off);
+      if (lane >= off) cum += t;
+    }
+    const bool defer = (deg > 0) && (is_long || cum > kItemCap);
+    const unsigned defer_mask = __ballot_sync(0xffffffffu, defer);
+    if (lane == 0) mask[grp] = defer_mask;
+    if (defer) {
+      const int64_t nseg = (deg64 + kSeg - 1) / kSeg;
+      const unsigned seg0 = atomicAdd(&counters[1], (unsigned)nseg);
+      int64_t slot0 = -1;
+      unsigned lr = 0;
+      if (nseg > 1) {
+        slot0 = atomicAdd(&counters[3], (unsigned)nseg);
+        lr = atomicAdd(&counters[2], 1u);
+        if ((int64_t)lr < long_cap) {
+          LongRow L;
+          L.row_b = r0 + lane;
+          L.first_slot = slot0;
+          L.nseg_count = (nseg << 40) | deg64;
+          longs[lr] = L;
+        }
+      }
+      for (int64_t sgi = 0; sgi < nseg; sgi++) {
+        if ((int64_t)seg0 + sgi < seg_cap) {
+          Segment S;
+          S.row_b = r0 + lane;
+          S.start = rp0 + sgi * kSeg;
+          S.end = min(rp1, S.start + kSeg);
+          S.slot = slot0 < 0 ? -1 : slot0 + sgi;
+          segs[seg0 + sgi] = S;
+          seg_lr[seg0 + sgi] = lr;
+        }
+      }
+    }
+  }
+}
+
+struct PlanLayout {
+  size_t header, mask, segs, seg_lr, longs, total;
+  int64_t seg_cap, long_cap;
+};
+static inline PlanLayout plan_layout(int64_t M, int64_t E) {
+  PlanLayout L;
+  const WsLayout W = ws_layout(1, 1, E, false, false);
+  L.seg_cap = W.seg_cap;
+  L.long_cap = W.long_cap;
+  size_t off = 0;
+  L.header = off; off += 256;
+  L.mask = off; off += align_up((size_t)((M + 31) / 32 + 1) * 4, 256);
+  L.segs = off; off += align_up((size_t)L.seg_cap * sizeof(Segment), 256);
+  L.seg_lr = off; off += align_up((size_t)L.seg_cap * 4, 256);
+  L.longs = off; off += align_up((size_t)L.long_cap * sizeof(LongRow), 256);
+  L.total = off;
+  return L;
+}
+struct PlannedWs {
+  size_t counters, long_done, part_val, part_arg, total;
+};
+static inline PlannedWs planned_ws(int64_t K, int64_t n_long, int64_t n_slot, bool arg) {
+  PlannedWs L;
+  size_t off = 0;
+  L.counters = off; off += 256;
+  L.long_done = off; off += align_up((size_t)(n_long > 0 ? n_long : 1) * 4, 256);
+  L.part_val = off; off += align_up((size_t)(n_slot > 0 ? n_slot : 1) * (size_t)K * sizeof(float), 256);
+  L.part_arg = off; off += arg ? align_up((size_t)(n_slot > 0 ? n_slot : 1) * (size_t)K * sizeof(int64_t), 256) : 0;
+  L.total = off;
+  return L;
 }
 
 template <typename T, int RED>
@@ -929,6 +1137,7 @@ extern "C" int tsb200_spmm_fw(const int64_t* rowptr, const int64_t* col, const v
     p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = arg_out;
     p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
     p.partial = nullptr; p.acc_mode = 0;
+    p.plan_mask = nullptr; p.seg_lr = nullptr; p.long_done = nullptr; p.n_seg = 0; p.n_long = 0;
     choose_pin(p, (size_t)B * N * K * dtype_size(dtype));
     p.counters = (unsigned int*)(ws + L.counters);
     p.segs = (Segment*)(ws + L.segs);
@@ -978,6 +1187,7 @@ extern "C" int tsb200_spmm_fw_acc(const int64_t* rowptr, const int64_t* col, con
   p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = nullptr;
   p.B = B; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
   p.partial = partial; p.acc_mode = acc_mode;
+  p.plan_mask = nullptr; p.seg_lr = nullptr; p.long_done = nullptr; p.n_seg = 0; p.n_long = 0;
   choose_pin(p, (size_t)B * N * K * dtype_size(dtype));
   p.counters = (unsigned int*)(ws + L.counters);
   p.segs = (Segment*)(ws + L.segs);
@@ -989,6 +1199,89 @@ extern "C" int tsb200_spmm_fw_acc(const int64_t* rowptr, const int64_t* col, con
     case TSB200_F32: return dispatch_shape<float, R_SUM, true>(p, st);
     case TSB200_F16: return dispatch_shape<__half, R_SUM, true>(p, st);
     case TSB200_BF16: return dispatch_shape<__nv_bfloat16, R_SUM, true>(p, st);
+  }
+  return TSB200_ERR_UNSUPPORTED;
+}
+
+// ---- planned SpMM: the segment structure of a matrix is computed once and reused by every product --------------
+extern "C" size_t tsb200_spmm_plan_bytes(int64_t M, int64_t E) {
+  if (M < 0 || E < 0) return 0;
+  return plan_layout(M, E).total;
+}
+
+extern "C" int tsb200_spmm_plan(const int64_t* rowptr, int64_t M, int64_t E, void* plan, size_t plan_bytes,
+                                int64_t* counts_host, void* stream) {
+  if (M < 0 || E < 0 || !rowptr || !plan) return TSB200_ERR_INVALID_ARG;
+  const PlanLayout L = plan_layout(M, E);
+  if (plan_bytes < L.total) return TSB200_ERR_WORKSPACE;
+  if ((uintptr_t)plan & 255) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* pl = (char*)plan;
+  TSB_CUDA_TRY(cudaMemsetAsync(pl + L.header, 0, 256, st));
+  if (M > 0) {
+    int64_t blocks = (((M + 31) / 32) * 32 + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    spmm_plan_kernel<<<(int)blocks, 256, 0, st>>>(rowptr, M, (uint32_t*)(pl + L.mask), (Segment*)(pl + L.segs),
+                                                 (uint32_t*)(pl + L.seg_lr), (LongRow*)(pl + L.longs),
+                                                 (unsigned int*)(pl + L.header), L.seg_cap, L.long_cap);
+    TSB_LAUNCH_CHECK();
+  }
+  if (counts_host) {  // [n_seg, n_long, n_slot] as uint32 counters 1..3 of the header; the caller widens them
+    unsigned int h[4] = {0, 0, 0, 0};
+    TSB_CUDA_TRY(cudaMemcpyAsync(h, pl + L.header, 16, cudaMemcpyDeviceToHost, st));
+    TSB_CUDA_TRY(cudaStreamSynchronize(st));
+    counts_host[0] = h[1];
+    counts_host[1] = h[2];
+    counts_host[2] = h[3];
+  }
+  return 0;
+}
+
+extern "C" size_t tsb200_spmm_fw_planned_workspace_bytes(int64_t K, int64_t n_long, int64_t n_slot, int reduce) {
+  if (K < 0 || n_long < 0 || n_slot < 0) return 0;
+  return planned_ws(K, n_long, n_slot, reduce == TSB200_MIN || reduce == TSB200_MAX).total;
+}
+
+extern "C" int tsb200_spmm_fw_planned(const int64_t* rowptr, const int64_t* col, const void* value, const void* mat,
+                                      void* out, int64_t* arg_out, int64_t M, int64_t N, int64_t K, int64_t E,
+                                      int dtype, int reduce, const void* plan, size_t plan_bytes, int64_t n_seg,
+                                      int64_t n_long, int64_t n_slot, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  if (M < 0 || N < 0 || K < 0 || E <= 0 || n_seg < 0 || n_long < 0 || n_slot < 0) return TSB200_ERR_INVALID_ARG;
+  if (reduce < TSB200_SUM || reduce > TSB200_MAX) return TSB200_ERR_INVALID_ARG;
+  const bool arg = (reduce == TSB200_MIN || reduce == TSB200_MAX);
+  if (M * K == 0) return 0;
+  if (!rowptr || !col || !mat || !out || !plan || (arg && !arg_out)) return TSB200_ERR_INVALID_ARG;
+  if (!vec_eligible(dtype, K, E, N, value, mat, out, col, arg_out)) return TSB200_ERR_UNSUPPORTED;
+  const PlanLayout PL = plan_layout(M, E);
+  if (plan_bytes < PL.total) return TSB200_ERR_WORKSPACE;
+  if (n_seg > PL.seg_cap || n_long > PL.long_cap) return TSB200_ERR_INVALID_ARG;
+  const PlannedWs W = planned_ws(K, n_long, n_slot, arg);
+  if (!workspace || workspace_bytes < W.total) return TSB200_ERR_WORKSPACE;
+  if (((uintptr_t)workspace & 255) || ((uintptr_t)plan & 255)) return TSB200_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const char* pl = (const char*)plan;
+  SpmmParams p;
+  p.rowptr = rowptr; p.col = col; p.value = value; p.mat = mat; p.out = out; p.arg_out = arg_out;
+  p.B = 1; p.M = M; p.N = N; p.K = K; p.E = E; p.k0 = 0; p.mean = 0; p.item_shift = 5;
+  p.partial = nullptr; p.acc_mode = 0;
+  choose_pin(p, (size_t)N * K * dtype_size(dtype));
+  p.counters = (unsigned int*)(ws + W.counters);
+  p.long_done = (uint32_t*)(ws + W.long_done);   // directly behind the counters: one memset clears both
+  p.segs = (Segment*)(pl + PL.segs);
+  p.longs = (LongRow*)(pl + PL.longs);
+  p.seg_lr = (const uint32_t*)(pl + PL.seg_lr);
+  p.plan_mask = (const uint32_t*)(pl + PL.mask);
+  p.n_seg = n_seg; p.n_long = n_long;
+  p.part_val = ws + W.part_val;
+  p.part_arg = arg ? (int64_t*)(ws + W.part_arg) : nullptr;
+  p.seg_cap = PL.seg_cap; p.long_cap = PL.long_cap; p.slot_cap = n_slot;
+  switch (dtype) {
+    case TSB200_F32: return dispatch_red_vec<float, true>(p, reduce, st);
+    case TSB200_F16: return dispatch_red_vec<__half, true>(p, reduce, st);
+    case TSB200_BF16: return dispatch_red_vec<__nv_bfloat16, true>(p, reduce, st);
   }
   return TSB200_ERR_UNSUPPORTED;
 }

@@ -8,6 +8,7 @@ reference's CHECK_CUDA, csrc/cuda/utils.cuh:5-6) — there is no CPU path.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
 from typing import Optional, Tuple
@@ -90,10 +91,64 @@ def _i64(t: Tensor, name: str) -> Tensor:
 # --------------------------------------------------------------------------------------------------
 # SpMM forward / value gradient / fused min-max backward
 # --------------------------------------------------------------------------------------------------
+class SpmmPlan:
+    """The segment structure of one CSR matrix (tsb200_spmm_plan): which rows are cut into segments, the segment list
+    and the multi-segment rows. Depends on `rowptr` only — build it once per matrix and pass it to `spmm_fw`."""
+    __slots__ = ("data", "M", "E", "n_seg", "n_long", "n_slot")
+
+    def __init__(self, rowptr: Tensor, E: int):
+        _check_cuda(rowptr, "rowptr")
+        rowptr = _i64(rowptr, "rowptr")
+        self.M, self.E = rowptr.numel() - 1, int(E)
+        dev = rowptr.device
+        with _on_device(dev):
+            nbytes = lib.tsb200_spmm_plan_bytes(self.M, self.E)
+            self.data = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            counts = (ctypes.c_int64 * 3)()
+            check(lib.tsb200_spmm_plan(_p(rowptr), self.M, self.E, _p(self.data), nbytes, counts, _stream(dev)),
+                  "tsb200_spmm_plan")
+        self.n_seg, self.n_long, self.n_slot = int(counts[0]), int(counts[1]), int(counts[2])
+
+
+def spmm_plan(rowptr: Tensor, E: int) -> SpmmPlan:
+    return SpmmPlan(rowptr, E)
+
+
+# Plans are structure-only, so they are kept per `rowptr` tensor like the reference keeps csr2csc / colptr per storage:
+# the second product with the same rowptr builds the plan (0.2 ms + one stream synchronisation, like the first csr2csc),
+# every later one uses it. The key is the tensor's storage, offset, extent and version counter; the entry holds a
+# reference to the storage, so its address cannot be recycled for another tensor while the entry lives.
+_PLAN_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+_PLAN_CACHE_MAX = 16
+
+
+def _auto_plan(rowptr: Tensor, E: int) -> Optional[SpmmPlan]:
+    if os.environ.get("TSB200_AUTO_PLAN", "1") == "0":
+        return None
+    try:
+        st = rowptr.untyped_storage()
+        key = (st._cdata, rowptr.storage_offset(), rowptr.numel(), rowptr._version, int(E), rowptr.device.index)
+    except RuntimeError:      # e.g. inference tensors keep no version counter
+        return None
+    ent = _PLAN_CACHE.get(key)
+    if ent is None:
+        _PLAN_CACHE[key] = [st, None]
+        while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+            _PLAN_CACHE.popitem(last=False)
+        return None
+    _PLAN_CACHE.move_to_end(key)
+    if ent[1] is None:
+        if torch.cuda.is_current_stream_capturing():   # building a plan synchronises the stream
+            return None
+        ent[1] = SpmmPlan(rowptr, E)
+    return ent[1]
+
+
 def spmm_fw(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor,
-            reduce: str) -> Tuple[Tensor, Optional[Tensor]]:
+            reduce: str, plan: Optional[SpmmPlan] = None) -> Tuple[Tensor, Optional[Tensor]]:
     """`spmm_fw(rowptr, col, optional_value, mat, reduce) -> (out, arg_out?)`
-    (csrc/spmm.cpp:22-35; checks follow csrc/cuda/spmm_cuda.cu:97-110)."""
+    (csrc/spmm.cpp:22-35; checks follow csrc/cuda/spmm_cuda.cu:97-110). With a `plan` (spmm_plan(rowptr, E)) the
+    product is one memset + one kernel (tsb200_spmm_fw_planned); results are the same."""
     _check_cuda(rowptr, "rowptr")
     _check_cuda(col, "col")
     if value is not None:
@@ -131,6 +186,18 @@ def spmm_fw(rowptr: Tensor, col: Tensor, value: Optional[Tensor], mat: Tensor,
             arg_out.fill_(0)
         return out, arg_out
     with _on_device(dev):
+        plannable = B == 1 and dt in (0, 2, 3) and (K * mat.element_size()) % 16 == 0
+        if plan is None and plannable:
+            plan = _auto_plan(rowptr, E)
+        if plan is not None and plannable and plan.M == M and plan.E == E:
+            nws = lib.tsb200_spmm_fw_planned_workspace_bytes(K, plan.n_long, plan.n_slot, red)
+            ws = _workspace(nws, dev)
+            rc = lib.tsb200_spmm_fw_planned(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(arg_out), M, N, K, E,
+                                            dt, red, _p(plan.data), plan.data.numel(), plan.n_seg, plan.n_long,
+                                            plan.n_slot, _p(ws), nws, _stream(dev))
+            if rc != -2:   # TSB200_ERR_UNSUPPORTED (alignment): fall through to the unplanned call
+                check(rc, "tsb200_spmm_fw_planned")
+                return out, arg_out
         nws = lib.tsb200_spmm_fw_workspace_bytes(B, M, K, E, dt, red)
         ws = _workspace(nws, dev)
         check(lib.tsb200_spmm_fw(_p(rowptr), _p(col), _p(value), _p(mat), _p(out), _p(arg_out),

@@ -322,3 +322,46 @@ def test_pipelined_row_sharded_spmm_single_rank(oracle, split):
         xs = pipe.to_sliced(x.to(DEV))
         assert torch.equal(pipe.from_sliced(xs).cpu(), x)
         assert torch.equal(pipe.from_sliced(pipe.forward_sliced(xs)), y)
+
+
+@pytest.mark.parametrize("dtype,K,reduce", [(torch.bfloat16, 128, "sum"), (torch.float32, 256, "max"),
+                                            (torch.float32, 32, "sum"), (torch.float16, 64, "mean"),
+                                            (torch.bfloat16, 256, "min"), (torch.float32, 128, "sum")])
+@pytest.mark.parametrize("has_value", [True, False])
+def test_planned_spmm_matches_unplanned_and_oracle(oracle, dtype, K, reduce, has_value):
+    """tsb200_spmm_plan + tsb200_spmm_fw_planned (one memset + one kernel: row items, then the plan's segments drained
+    by the same warps, multi-segment rows combined by the last finisher) on a power-law matrix with empty rows, rows
+    of exactly / just over the segment length and rows of thousands of nnz — against the unplanned call and the oracle."""
+    M, N = 5000, 4096
+    row, rowptr, col = random_csr(M, N, 14, seed=31, power_law=True, empty_rows=(0, 1, 4999),
+                                  long_rows=[(3, 4000), (4, 1025), (5, 257), (6, 256), (40, 600), (41, 600)])
+    g = torch.Generator().manual_seed(32)
+    value = torch.randn(col.numel(), generator=g).to(dtype) if has_value else None
+    x = torch.randn(N, K, generator=g).to(dtype)
+    d_rowptr, d_col = rowptr.to(DEV), col.to(DEV)
+    d_value = None if value is None else value.to(DEV)
+    plan = ops.spmm_plan(d_rowptr, col.numel())
+    assert plan.n_seg > 0 and plan.n_long > 0 and plan.n_slot >= 2 * plan.n_long
+    out_p, arg_p = ops.spmm_fw(d_rowptr, d_col, d_value, x.to(DEV), reduce, plan=plan)
+    out_u, arg_u = ops.spmm_fw(d_rowptr, d_col, d_value, x.to(DEV), reduce)
+    ref, ref_arg = oracle.spmm(rowptr, col, value, x, reduce)
+    if reduce in ("min", "max"):
+        assert torch.equal(out_p, out_u) and torch.equal(arg_p, arg_u)
+        assert torch.equal(out_p.cpu(), ref) and torch.equal(arg_p.cpu(), ref_arg)
+    else:
+        vf = None if value is None else value.float().abs()
+        bound, _ = oracle.spmm(rowptr, col, vf, x.float().abs(), "sum")
+        if reduce == "mean":
+            bound = bound / (rowptr[1:] - rowptr[:-1]).clamp(min=1).view(-1, 1)
+        fref, _ = oracle.spmm(rowptr, col, None if value is None else value.float(), x.float(), reduce)
+        tol = 1e-5 if dtype == torch.float32 else 1e-2
+        assert ((out_p.cpu().float() - fref).abs() <= tol * bound + 1e-30).all()
+        assert ((out_p.float() - out_u.float()).abs().cpu() <= tol * bound + 1e-30).all()
+    # a matrix without long rows: the plan is empty and the call is a single kernel
+    r2, rp2, c2 = random_csr(300, 200, 5, seed=33)
+    plan2 = ops.spmm_plan(rp2.to(DEV), c2.numel())
+    assert plan2.n_seg == 0 and plan2.n_long == 0
+    x2 = torch.randn(200, K, generator=g).to(dtype)
+    o2, a2 = ops.spmm_fw(rp2.to(DEV), c2.to(DEV), None, x2.to(DEV), reduce, plan=plan2)
+    o3, a3 = ops.spmm_fw(rp2.to(DEV), c2.to(DEV), None, x2.to(DEV), reduce)
+    assert torch.equal(o2, o3) and (a2 is None or torch.equal(a2, a3))
